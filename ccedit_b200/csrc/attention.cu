@@ -1,0 +1,402 @@
+// Attention kernels.
+//  * flash_attn_kernel: softmax(q k^T * scale) v with an online softmax over 64-key tiles staged in shared memory
+//    (cp.async double buffering), warp-level tensor-core MMAs, fp32 accumulation.  Replaces the
+//    F.scaled_dot_product_attention call at attention.py:444-448 for spatial self-attention (keys = the frame's own
+//    tokens), text cross-attention (77 keys shared by all frames of a batch entry) and the cross-frame "center_self"
+//    block (two key segments: centre-frame tokens then own tokens, attention.py:1323-1336).
+//  * temporal_attn_kernel: one warp per (pixel, head), attends over the T frames of that pixel without ever
+//    materialising the "(b h w) t c" transposition the reference performs (attention.py:1172-1194).
+#include "common.cuh"
+#include "../../include/ccedit_b200.h"
+
+#include <atomic>
+
+namespace ccedit {
+extern std::atomic<long long> g_launch_count;
+
+constexpr int kFaBM = 128;     // queries per CTA (8 warps x 16 rows)
+constexpr int kFaBN = 64;      // keys per tile
+constexpr int kFaThreads = 256;
+
+struct FaParams {
+  const __half* q;
+  long long ldq, q_fs;
+  __half* o;
+  long long ldo, o_fs;
+  int nseg;
+  const __half* k[2];
+  const __half* v[2];
+  long long ldk[2], ldv[2], kv_fs[2];
+  int lkv[2], kv_div[2], kv_mul[2], kv_add[2];
+  int lq, d;
+  float scale_log2;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(kFaThreads) flash_attn_kernel(const __grid_constant__ FaParams p) {
+  constexpr int DS = DP + 8;        // smem row stride in halves (odd multiple of 16 B => conflict-free ldmatrix)
+  constexpr int KSTEPS = DP / 16;   // k-steps of QK^T
+  constexpr int NT_O = DP / 8;      // n-tiles of the output
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  __half* sQ = reinterpret_cast<__half*>(fa_smem);          // [128][DS]
+  __half* sK = sQ + kFaBM * DS;                               // [2][64][DS]
+  __half* sV = sK + 2 * kFaBN * DS;                           // [2][64][DS]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * kFaBM, head = blockIdx.y, f = blockIdx.z;
+  const int d = p.d;
+  const int chunks = d >> 3;        // 16-byte chunks per row actually present in global memory
+  constexpr int CH = DP / 8;        // chunks per padded row
+
+  // zero the padding chunks once (cp.async never touches them)
+  if (chunks < CH) {
+    const int padc = CH - chunks;
+    for (int i = tid; i < (kFaBM + 4 * kFaBN) * padc; i += kFaThreads) {
+      const int r = i / padc, c = chunks + i % padc;
+      *reinterpret_cast<uint4*>(sQ + r * DS + c * 8) = make_uint4(0, 0, 0, 0);  // sQ,sK,sV are contiguous
+    }
+  }
+
+  const __half* qbase = p.q + static_cast<long long>(f) * p.q_fs + static_cast<long long>(head) * d;
+  for (int i = tid; i < kFaBM * chunks; i += kFaThreads) {
+    const int r = i / chunks, c = i % chunks;
+    const bool ok = (q0 + r) < p.lq;
+    const __half* src = qbase + static_cast<long long>(ok ? q0 + r : 0) * p.ldq + c * 8;
+    cp_async_16(smem_u32(sQ + r * DS + c * 8), src, ok);
+  }
+
+  // tile bookkeeping over the (up to two) key segments
+  const int ntile0 = (p.lkv[0] + kFaBN - 1) / kFaBN;
+  const int ntile1 = p.nseg > 1 ? (p.lkv[1] + kFaBN - 1) / kFaBN : 0;
+  const int ntiles = ntile0 + ntile1;
+
+  auto load_kv = [&](int it, int buf) {
+    const int seg = it < ntile0 ? 0 : 1;
+    const int k0 = (seg == 0 ? it : it - ntile0) * kFaBN;
+    const long long kvf = static_cast<long long>(f / p.kv_div[seg]) * p.kv_mul[seg] + p.kv_add[seg];
+    const __half* kb = p.k[seg] + kvf * p.kv_fs[seg] + static_cast<long long>(head) * d;
+    const __half* vb = p.v[seg] + kvf * p.kv_fs[seg] + static_cast<long long>(head) * d;
+    __half* dK = sK + buf * kFaBN * DS;
+    __half* dV = sV + buf * kFaBN * DS;
+    for (int i = tid; i < kFaBN * chunks; i += kFaThreads) {
+      const int r = i / chunks, c = i % chunks;
+      const bool ok = (k0 + r) < p.lkv[seg];
+      const long long rr = ok ? k0 + r : 0;
+      cp_async_16(smem_u32(dK + r * DS + c * 8), kb + rr * p.ldk[seg] + c * 8, ok);
+      cp_async_16(smem_u32(dV + r * DS + c * 8), vb + rr * p.ldv[seg] + c * 8, ok);
+    }
+  };
+
+  load_kv(0, 0);
+  cp_async_commit();
+
+  float o_acc[NT_O][4];
+#pragma unroll
+  for (int i = 0; i < NT_O; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qf[KSTEPS][4];
+
+  for (int it = 0; it < ntiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < ntiles) {
+      load_kv(it + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (it == 0) {
+      // Q fragments: warp's 16 rows, A-operand layout via ldmatrix.x4
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const int r = warp * 16 + (lane & 15);
+        const int c = ks * 16 + (lane >> 4) * 8;
+        ldmatrix_x4(qf[ks], smem_u32(sQ + r * DS + c));
+      }
+    }
+    const __half* tK = sK + buf * kFaBN * DS;
+    const __half* tV = sV + buf * kFaBN * DS;
+
+    // ---- S = Q K^T (16 x 64 per warp) ----
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {  // pairs of 8-key n-tiles
+        uint32_t kf[4];
+        const int r = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(kf, smem_u32(tK + r * DS + c));
+        const uint32_t b0[2] = {kf[0], kf[1]}, b1[2] = {kf[2], kf[3]};
+        mma_m16n8k16(s[2 * np], qf[ks], b0);
+        mma_m16n8k16(s[2 * np + 1], qf[ks], b1);
+      }
+    }
+    // ---- mask keys beyond the segment end, scale ----
+    const int seg = it < ntile0 ? 0 : 1;
+    const int k0 = (seg == 0 ? it : it - ntile0) * kFaBN;
+    const int kvalid = p.lkv[seg] - k0;  // number of valid keys in this tile (may exceed 64)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = nt * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = (col + (e & 1)) < kvalid;
+        const float val = ok ? s[nt][e] * p.scale_log2 : -INFINITY;
+        s[nt][e] = val;
+        mx[e >> 1] = fmaxf(mx[e >> 1], val);
+      }
+    }
+    float alpha[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      const float m_new = fmaxf(m_run[h], mx[h]);  // finite: every tile has at least one valid key
+      alpha[h] = exp2f(m_run[h] - m_new);
+      m_run[h] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[4][4];  // P as A fragments for 4 k-steps of 16 keys
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] - m_run[0]), p1 = exp2f(s[nt][1] - m_run[0]);
+      const float p2 = exp2f(s[nt][2] - m_run[1]), p3 = exp2f(s[nt][3] - m_run[1]);
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
+      __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+      pf[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&h01);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&h23);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) l_run[h] = l_run[h] * alpha[h] + rs[h];
+#pragma unroll
+    for (int i = 0; i < NT_O; ++i) {
+      o_acc[i][0] *= alpha[0];
+      o_acc[i][1] *= alpha[0];
+      o_acc[i][2] *= alpha[1];
+      o_acc[i][3] *= alpha[1];
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {       // 16 keys per step
+#pragma unroll
+      for (int np = 0; np < NT_O / 2; ++np) {  // pairs of 8-wide d tiles
+        uint32_t vf[4];
+        const int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = np * 16 + (lane >> 4) * 8;
+        ldmatrix_x4_trans(vf, smem_u32(tV + r * DS + c));
+        const uint32_t b0[2] = {vf[0], vf[1]}, b1[2] = {vf[2], vf[3]};
+        mma_m16n8k16(o_acc[2 * np], pf[kk], b0);
+        mma_m16n8k16(o_acc[2 * np + 1], pf[kk], b1);
+      }
+    }
+    __syncthreads();  // all warps done with this buffer before it is refilled
+  }
+
+  // ---- finalise: O / l, stage through this warp's own Q rows, coalesced 16-byte stores ----
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+    l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+  }
+  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+  __half* sO = sQ + warp * 16 * DS;
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < NT_O; ++nt) {
+    const int col = nt * 8 + (lane & 3) * 2;
+    const int r = lane >> 2;
+    *reinterpret_cast<__half2*>(sO + r * DS + col) = __floats2half2_rn(o_acc[nt][0] * inv0, o_acc[nt][1] * inv0);
+    *reinterpret_cast<__half2*>(sO + (r + 8) * DS + col) = __floats2half2_rn(o_acc[nt][2] * inv1, o_acc[nt][3] * inv1);
+  }
+  __syncwarp();
+  __half* obase = p.o + static_cast<long long>(f) * p.o_fs + static_cast<long long>(head) * d;
+  for (int i = lane; i < 16 * chunks; i += 32) {
+    const int r = i / chunks, c = i % chunks;
+    const int qr = q0 + warp * 16 + r;
+    if (qr < p.lq)
+      *reinterpret_cast<uint4*>(obase + static_cast<long long>(qr) * p.ldo + c * 8) =
+          *reinterpret_cast<const uint4*>(sO + r * DS + c * 8);
+  }
+}
+
+template <int DP>
+static int launch_fa(const FaParams& p, int frames, int heads, cudaStream_t st) {
+  constexpr int DS = DP + 8;
+  const int smem = (kFaBM + 4 * kFaBN) * DS * 2;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_last_error("ccedit_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CCEDIT_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  dim3 grid((p.lq + kFaBM - 1) / kFaBM, heads, frames);
+  flash_attn_kernel<DP><<<grid, kFaThreads, smem, st>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_attention");
+  return CCEDIT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// temporal attention: grid (B*HW, heads/wpb); one warp per head.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void temporal_attn_kernel(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k,
+                                     long long ldk, const __half* __restrict__ v, long long ldv, __half* __restrict__ o,
+                                     long long ldo, int T, int HW, int d, float scale_log2) {
+  extern __shared__ __align__(16) uint8_t ta_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int head = blockIdx.y * wpb + warp;
+  const long long pix = blockIdx.x;  // b*HW + hw
+  const int b = static_cast<int>(pix / HW), hw = static_cast<int>(pix % HW);
+  const int dw = d >> 1;        // 32-bit words per row
+  const int rs = dw + 1;        // padded row stride (odd) in words
+  uint32_t* sq = reinterpret_cast<uint32_t*>(ta_smem) + static_cast<size_t>(warp) * 3 * T * rs;
+  uint32_t* sk = sq + T * rs;
+  uint32_t* sv = sk + T * rs;
+  const long long row0 = (static_cast<long long>(b) * T) * HW + hw;  // row index of frame 0; frame t adds t*HW
+  for (int i = lane; i < T * dw; i += 32) {
+    const int t = i / dw, w = i % dw;
+    const long long row = row0 + static_cast<long long>(t) * HW;
+    sq[t * rs + w] = __ldg(reinterpret_cast<const uint32_t*>(q + row * ldq + head * d) + w);
+    sk[t * rs + w] = __ldg(reinterpret_cast<const uint32_t*>(k + row * ldk + head * d) + w);
+    sv[t * rs + w] = __ldg(reinterpret_cast<const uint32_t*>(v + row * ldv + head * d) + w);
+  }
+  __syncwarp();
+  const int j0 = lane, j1 = lane + 32;  // key slots of this lane (T <= 64)
+  for (int i = 0; i < T; ++i) {
+    float s0 = 0.f, s1 = 0.f;
+    const uint32_t* qi = sq + i * rs;
+    if (j0 < T) {
+      const uint32_t* kj = sk + j0 * rs;
+      for (int w = 0; w < dw; ++w) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&qi[w]));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&kj[w]));
+        s0 = fmaf(a.x, c.x, s0);
+        s0 = fmaf(a.y, c.y, s0);
+      }
+    }
+    if (j1 < T) {
+      const uint32_t* kj = sk + j1 * rs;
+      for (int w = 0; w < dw; ++w) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&qi[w]));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&kj[w]));
+        s1 = fmaf(a.x, c.x, s1);
+        s1 = fmaf(a.y, c.y, s1);
+      }
+    }
+    s0 = j0 < T ? s0 * scale_log2 : -INFINITY;
+    s1 = j1 < T ? s1 * scale_log2 : -INFINITY;
+    float m = fmaxf(s0, s1);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    const float p0 = exp2f(s0 - m), p1 = exp2f(s1 - m);
+    float l = p0 + p1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+    const float inv = 1.f / l;
+    const long long orow = row0 + static_cast<long long>(i) * HW;
+    uint32_t* op = reinterpret_cast<uint32_t*>(o + orow * ldo + head * d);
+    for (int w0 = 0; w0 < dw; w0 += 32) {
+      const int w = w0 + lane;
+      float ax = 0.f, ay = 0.f;
+      for (int j = 0; j < T; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
+        if (w < dw) {
+          const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(&sv[j * rs + w]));
+          ax = fmaf(pj, vv.x, ax);
+          ay = fmaf(pj, vv.y, ay);
+        }
+      }
+      if (w < dw) {
+        __half2 r = __floats2half2_rn(ax * inv, ay * inv);
+        op[w] = *reinterpret_cast<uint32_t*>(&r);
+      }
+    }
+  }
+}
+
+}  // namespace ccedit
+
+using namespace ccedit;
+
+extern "C" int ccedit_attention(const ccedit_attn_desc* a, void* stream) {
+  CCEDIT_CHECK_ARG(a != nullptr, "ccedit_attention: null descriptor");
+  CCEDIT_CHECK_ARG(a->q && a->o && a->nseg >= 1 && a->nseg <= 2, "ccedit_attention: bad q/o/nseg");
+  CCEDIT_CHECK_ARG(a->d > 0 && a->d % 8 == 0 && a->d <= 160, "ccedit_attention: head dim %d unsupported (multiple of 8, <=160)", a->d);
+  CCEDIT_CHECK_ARG(a->frames > 0 && a->lq > 0 && a->heads > 0, "ccedit_attention: empty problem");
+  CCEDIT_CHECK_ARG(a->ldq % 8 == 0 && a->ldo % 8 == 0 && a->q_frame_stride % 8 == 0 && a->o_frame_stride % 8 == 0,
+                   "ccedit_attention: q/o strides must be multiples of 8 elements");
+  FaParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = static_cast<const __half*>(a->q);
+  p.ldq = a->ldq;
+  p.q_fs = a->q_frame_stride;
+  p.o = static_cast<__half*>(a->o);
+  p.ldo = a->ldo;
+  p.o_fs = a->o_frame_stride;
+  p.nseg = a->nseg;
+  for (int s = 0; s < a->nseg; ++s) {
+    CCEDIT_CHECK_ARG(a->k[s] && a->v[s] && a->lkv[s] > 0 && a->kv_div[s] > 0, "ccedit_attention: bad kv segment %d", s);
+    CCEDIT_CHECK_ARG(a->ldk[s] % 8 == 0 && a->ldv[s] % 8 == 0 && a->kv_frame_stride[s] % 8 == 0,
+                     "ccedit_attention: kv strides must be multiples of 8 elements");
+    p.k[s] = static_cast<const __half*>(a->k[s]);
+    p.v[s] = static_cast<const __half*>(a->v[s]);
+    p.ldk[s] = a->ldk[s];
+    p.ldv[s] = a->ldv[s];
+    p.kv_fs[s] = a->kv_frame_stride[s];
+    p.lkv[s] = a->lkv[s];
+    p.kv_div[s] = a->kv_div[s];
+    p.kv_mul[s] = a->kv_mul[s];
+    p.kv_add[s] = a->kv_add[s];
+  }
+  p.lq = a->lq;
+  p.d = a->d;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->d <= 16) return launch_fa<16>(p, a->frames, a->heads, st);
+  if (a->d <= 32) return launch_fa<32>(p, a->frames, a->heads, st);
+  if (a->d <= 48) return launch_fa<48>(p, a->frames, a->heads, st);
+  if (a->d <= 64) return launch_fa<64>(p, a->frames, a->heads, st);
+  if (a->d <= 80) return launch_fa<80>(p, a->frames, a->heads, st);
+  if (a->d <= 128) return launch_fa<128>(p, a->frames, a->heads, st);
+  return launch_fa<160>(p, a->frames, a->heads, st);
+}
+
+extern "C" int ccedit_temporal_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                         int64_t ldv, void* o, int64_t ldo, int32_t B, int32_t T, int32_t HW,
+                                         int32_t heads, int32_t d, float scale, void* stream) {
+  CCEDIT_CHECK_ARG(q && k && v && o, "ccedit_temporal_attention: null pointer");
+  CCEDIT_CHECK_ARG(B > 0 && T > 0 && T <= 64 && HW > 0 && heads > 0 && d > 0 && d % 2 == 0,
+                   "ccedit_temporal_attention: bad shape B=%d T=%d HW=%d heads=%d d=%d (T<=64)", B, T, HW, heads, d);
+  CCEDIT_CHECK_ARG(ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0, "ccedit_temporal_attention: odd stride");
+  const size_t per_warp = static_cast<size_t>(3) * T * (d / 2 + 1) * 4;
+  int wpb = 8;
+  while (wpb > 1 && (heads % wpb != 0 || per_warp * wpb > 200 * 1024)) wpb >>= 1;
+  CCEDIT_CHECK_ARG(per_warp * wpb <= 227 * 1024, "ccedit_temporal_attention: T*d too large for shared memory");
+  const size_t smem = per_warp * wpb;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_last_error("ccedit_temporal_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CCEDIT_ERR_CUDA;
+    }
+    smem_set = 227 * 1024;
+  }
+  dim3 grid(static_cast<unsigned>(static_cast<long long>(B) * HW), heads / wpb);
+  temporal_attn_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(q), ldq, static_cast<const __half*>(k), ldk, static_cast<const __half*>(v), ldv,
+      static_cast<__half*>(o), ldo, T, HW, d, scale * 1.4426950408889634f);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_temporal_attention");
+  return CCEDIT_OK;
+}

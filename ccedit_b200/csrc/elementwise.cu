@@ -1,0 +1,311 @@
+// Small / layout kernels of the CCEdit hot path (all HBM- or latency-bound; 16-byte vectorised where the layout allows).
+#include "common.cuh"
+#include "../../include/ccedit_b200.h"
+
+#include <atomic>
+
+namespace ccedit {
+extern std::atomic<long long> g_launch_count;
+
+// [B][Cin][T][H][W] -> [B][T][H][W][Cpad] fp16, v*mul+add, zero padded channels. One thread per pixel.
+template <typename SrcT>
+__global__ void ncthw_to_cl_kernel(const SrcT* __restrict__ src, __half* __restrict__ dst, int Cin, int T, long long HW,
+                                   int Cpad, float mul, float add, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // over B*T*HW
+  if (i >= total) return;
+  const long long hw = i % HW;
+  const long long bt = i / HW;
+  const int t = static_cast<int>(bt % T);
+  const long long b = bt / T;
+  __half* d = dst + i * Cpad;
+  for (int c0 = 0; c0 < Cpad; c0 += 8) {
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float v = 0.f;
+      if (c < Cin) v = static_cast<float>(src[((b * Cin + c) * T + t) * HW + hw]) * mul + add;
+      h[j] = __float2half_rn(v);
+    }
+    *reinterpret_cast<uint4*>(d + c0) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+// UNet tail: dst[b][c][t][hw] = y + bias_t[c] + sum wt[c][c'][dt] * silu(y[t+dt-1][c'])   (Cout <= 8)
+template <typename DstT>
+__global__ void out_temporal_kernel(const __half* __restrict__ y, int ldy, const float* __restrict__ wt,
+                                    const float* __restrict__ bias_t, DstT* __restrict__ dst, int Cout, int T,
+                                    long long HW, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // over B*T*HW
+  if (i >= total) return;
+  const long long hw = i % HW;
+  const long long bt = i / HW;
+  const int t = static_cast<int>(bt % T);
+  const long long b = bt / T;
+  float acc[8], cur[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  for (int dt = 0; dt < 3; ++dt) {
+    const int tt = t + dt - 1;
+    if (tt < 0 || tt >= T) continue;
+    const __half* yp = y + ((b * T + tt) * HW + hw) * ldy;
+    float s[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float v = c < Cout ? __half2float(yp[c]) : 0.f;
+      if (dt == 1) cur[c] = v;
+      s[c] = silu_f(v);
+    }
+    for (int c = 0; c < Cout; ++c)
+      for (int c2 = 0; c2 < Cout; ++c2) acc[c] += wt[(c * Cout + c2) * 3 + dt] * s[c2];
+  }
+  for (int c = 0; c < Cout; ++c)
+    dst[((b * Cout + c) * T + t) * HW + hw] = static_cast<DstT>(cur[c] + bias_t[c] + acc[c]);
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim,
+                                          float max_period) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= B * half) return;
+  const int b = i / half, k = i % half;
+  const float freq = expf(-logf(max_period) * static_cast<float>(k) / static_cast<float>(half));
+  const float arg = t[b] * freq;
+  out[b * dim + k] = cosf(arg);
+  out[b * dim + half + k] = sinf(arg);
+  if ((dim & 1) && k == 0) out[b * dim + dim - 1] = 0.f;
+}
+
+// out[m][n] = act_out(sum_k act_in(x[m][k]) w[n][k] + b[n]); one warp per n, M <= 8.
+__global__ void linear_small_kernel(const float* __restrict__ x, const __half* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ out, int M, int N, int K,
+                                    int act_in, int act_out) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.f;
+  const __half* wr = w + static_cast<long long>(n) * K;
+  for (int k0 = lane * 8; k0 < K; k0 += 256) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k0));
+    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+    float wf[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
+      wf[2 * j] = f.x;
+      wf[2 * j + 1] = f.y;
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float xv = x[m * K + k0 + j];
+          if (act_in) xv = xv / (1.f + expf(-xv));
+          acc[m] = fmaf(xv, wf[j], acc[m]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+  }
+  if (lane == 0) {
+    for (int m = 0; m < M; ++m) {
+      float v = acc[m] + (bias ? bias[n] : 0.f);
+      if (act_out) v = v / (1.f + expf(-v));
+      out[m * N + n] = v;
+    }
+  }
+}
+
+// [F][H][W][C] -> [F][4][H/2][W/2][C], plane = (h&1)*2 + (w&1); one thread per 16-byte vector
+__global__ void parity_split_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int nvec,
+                                    long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = static_cast<int>(i % nvec);
+  long long r = i / nvec;
+  const int w = static_cast<int>(r % W);
+  r /= W;
+  const int h = static_cast<int>(r % H);
+  const long long f = r / H;
+  const int plane = (h & 1) * 2 + (w & 1);
+  const int H2 = H / 2, W2 = W / 2;
+  y[(((f * 4 + plane) * H2 + (h >> 1)) * W2 + (w >> 1)) * nvec + cv] = __ldg(x + i);
+}
+
+// nearest x2: one thread per output vector
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int nvec,
+                                  long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = static_cast<int>(i % nvec);
+  long long r = i / nvec;
+  const int wo = static_cast<int>(r % (2 * W));
+  r /= (2 * W);
+  const int ho = static_cast<int>(r % (2 * H));
+  const long long f = r / (2 * H);
+  y[i] = __ldg(x + ((f * H + (ho >> 1)) * W + (wo >> 1)) * nvec + cv);
+}
+
+__device__ __forceinline__ uint4 add8(const uint4& a, const uint4& b) {
+  uint4 r;
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t rw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[j]));
+    const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[j]));
+    __half2 h = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+    rw[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  r.x = rw[0];
+  r.y = rw[1];
+  r.z = rw[2];
+  r.w = rw[3];
+  return r;
+}
+
+__global__ void add_rows_kernel(const __half* __restrict__ a, long long lda, const __half* __restrict__ b, long long ldb,
+                                __half* __restrict__ dst, long long ldd, int nvec, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = static_cast<int>(i % nvec);
+  const long long m = i / nvec;
+  uint4 va = __ldg(reinterpret_cast<const uint4*>(a + m * lda) + cv);
+  if (b) va = add8(va, __ldg(reinterpret_cast<const uint4*>(b + m * ldb) + cv));
+  reinterpret_cast<uint4*>(dst + m * ldd)[cv] = va;
+}
+
+__global__ void add_center_frame_kernel(__half* __restrict__ x, const __half* __restrict__ y, int T, long long HWnvec,
+                                        long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // over B*HW*nvec
+  if (i >= total) return;
+  const long long b = i / HWnvec, r = i % HWnvec;
+  uint4* xp = reinterpret_cast<uint4*>(x) + (b * T + T / 2) * HWnvec + r;
+  *xp = add8(*xp, __ldg(reinterpret_cast<const uint4*>(y) + i));
+}
+
+static inline unsigned blocks_for(long long total, int threads) {
+  return static_cast<unsigned>((total + threads - 1) / threads);
+}
+
+}  // namespace ccedit
+
+using namespace ccedit;
+
+extern "C" int ccedit_ncthw_to_cl(const void* src, int32_t src_f32, void* dst, int32_t B, int32_t Cin, int32_t T,
+                                  int32_t H, int32_t W, int32_t Cpad, float mul, float add, void* stream) {
+  CCEDIT_CHECK_ARG(src && dst, "ccedit_ncthw_to_cl: null pointer");
+  CCEDIT_CHECK_ARG(B > 0 && Cin > 0 && T > 0 && H > 0 && W > 0 && Cpad >= Cin && Cpad % 8 == 0,
+                   "ccedit_ncthw_to_cl: bad shape B=%d Cin=%d T=%d H=%d W=%d Cpad=%d", B, Cin, T, H, W, Cpad);
+  const long long HW = static_cast<long long>(H) * W, total = static_cast<long long>(B) * T * HW;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src_f32)
+    ncthw_to_cl_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const float*>(src),
+                                                                      static_cast<__half*>(dst), Cin, T, HW, Cpad, mul,
+                                                                      add, total);
+  else
+    ncthw_to_cl_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(src),
+                                                                       static_cast<__half*>(dst), Cin, T, HW, Cpad, mul,
+                                                                       add, total);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_ncthw_to_cl");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_out_temporal(const void* y, int32_t ldy, const float* wt, const float* bias_t, void* dst,
+                                   int32_t dst_f32, int32_t B, int32_t Cout, int32_t T, int32_t HW, void* stream) {
+  CCEDIT_CHECK_ARG(y && wt && bias_t && dst, "ccedit_out_temporal: null pointer");
+  CCEDIT_CHECK_ARG(B > 0 && Cout > 0 && Cout <= 8 && T > 0 && HW > 0 && ldy >= Cout,
+                   "ccedit_out_temporal: bad shape B=%d Cout=%d T=%d HW=%d ldy=%d", B, Cout, T, HW, ldy);
+  const long long total = static_cast<long long>(B) * T * HW;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dst_f32)
+    out_temporal_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(y), ldy, wt, bias_t,
+                                                                       static_cast<float*>(dst), Cout, T, HW, total);
+  else
+    out_temporal_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(y), ldy, wt, bias_t,
+                                                                        static_cast<__half*>(dst), Cout, T, HW, total);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_out_temporal");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_timestep_embedding(const float* t, float* out, int32_t B, int32_t dim, float max_period,
+                                         void* stream) {
+  CCEDIT_CHECK_ARG(t && out && B > 0 && dim >= 2, "ccedit_timestep_embedding: bad arguments");
+  const int total = B * (dim / 2);
+  timestep_embedding_kernel<<<blocks_for(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, B, dim,
+                                                                                                   max_period);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_timestep_embedding");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_linear_small(const float* x, const void* w, const float* b, float* out, int32_t M, int32_t N,
+                                   int32_t K, int32_t act_in, int32_t act_out, void* stream) {
+  CCEDIT_CHECK_ARG(x && w && out, "ccedit_linear_small: null pointer");
+  CCEDIT_CHECK_ARG(M >= 1 && M <= 8 && N > 0 && K > 0 && K % 8 == 0, "ccedit_linear_small: bad shape M=%d N=%d K=%d (M<=8, K%%8==0)", M, N, K);
+  const int wpb = 4;
+  linear_small_kernel<<<(N + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<const __half*>(w), b, out, M, N, K, act_in, act_out);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_linear_small");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_parity_split(const void* x, void* y, int32_t F, int32_t H, int32_t W, int32_t C, void* stream) {
+  CCEDIT_CHECK_ARG(x && y && F > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0,
+                   "ccedit_parity_split: bad shape F=%d H=%d W=%d C=%d (H, W even; C%%8==0)", F, H, W, C);
+  const int nvec = C / 8;
+  const long long total = static_cast<long long>(F) * H * W * nvec;
+  parity_split_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), H, W, nvec, total);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_parity_split");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_upsample_nearest2x(const void* x, void* y, int32_t F, int32_t H, int32_t W, int32_t C,
+                                         void* stream) {
+  CCEDIT_CHECK_ARG(x && y && F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0,
+                   "ccedit_upsample_nearest2x: bad shape F=%d H=%d W=%d C=%d", F, H, W, C);
+  const int nvec = C / 8;
+  const long long total = static_cast<long long>(F) * H * W * 4 * nvec;
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), H, W, nvec, total);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_upsample_nearest2x");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_add_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void* dst, int64_t ldd,
+                               int64_t M, int32_t C, void* stream) {
+  CCEDIT_CHECK_ARG(a && dst && M > 0 && C > 0 && C % 8 == 0 && lda % 8 == 0 && ldd % 8 == 0 && (!b || ldb % 8 == 0),
+                   "ccedit_add_rows: bad arguments M=%lld C=%d", (long long)M, C);
+  const int nvec = C / 8;
+  const long long total = M * nvec;
+  add_rows_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(a), lda, static_cast<const __half*>(b), ldb, static_cast<__half*>(dst), ldd, nvec,
+      total);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_add_rows");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_add_center_frame(void* x, const void* y, int32_t B, int32_t T, int32_t HW, int32_t C,
+                                       void* stream) {
+  CCEDIT_CHECK_ARG(x && y && B > 0 && T > 0 && HW > 0 && C > 0 && C % 8 == 0, "ccedit_add_center_frame: bad arguments");
+  const long long HWnvec = static_cast<long long>(HW) * (C / 8), total = B * HWnvec;
+  add_center_frame_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__half*>(x), static_cast<const __half*>(y), T, HWnvec, total);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_add_center_frame");
+  return CCEDIT_OK;
+}

@@ -1,0 +1,323 @@
+// GroupNorm (spatial: per frame; temporal: per pixel over T) and LayerNorm, fp16 in/out, fp32 statistics.
+// All three are HBM-bound: one read + one write of the activation (the spatial flavour reads twice: statistics, apply).
+// Reference call sites: util.py:296-302 (eps 1e-5), attention.py:153-156 (eps 1e-6), attention.py:667-669 (LayerNorm);
+// the temporal reduction shape comes from openaimodel.py:157 ("(b h w) c t" => statistics over (C/32, T) per pixel).
+#include "common.cuh"
+#include "../../include/ccedit_b200.h"
+
+#include <atomic>
+
+namespace ccedit {
+extern std::atomic<long long> g_launch_count;
+int device_sm_count();
+
+constexpr int kGroups = 32;
+constexpr int kMaxSplit = 32;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+  __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+
+// accumulate the 8 per-channel (sum, sumsq) of one thread into per-group shared accumulators
+__device__ __forceinline__ void flush_groups(const float (&s)[8], const float (&q)[8], int c0, int cpg, float* sg) {
+  int g = c0 / cpg;
+  float rs = 0.f, rq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int gj = (c0 + j) / cpg;
+    if (gj != g) {
+      atomicAdd(&sg[2 * g], rs);
+      atomicAdd(&sg[2 * g + 1], rq);
+      rs = 0.f;
+      rq = 0.f;
+      g = gj;
+    }
+    rs += s[j];
+    rq += q[j];
+  }
+  atomicAdd(&sg[2 * g], rs);
+  atomicAdd(&sg[2 * g + 1], rq);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// spatial GroupNorm: statistics
+// grid (nsplit, F); block = nvec * rpi threads (nvec = C/8 vectors per row, rpi rows per iteration)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gn_spatial_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, int HW, int C,
+                                        int nvec, int rpi, int nsplit) {
+  __shared__ float sg[2 * kGroups];
+  const int f = blockIdx.y, split = blockIdx.x;
+  if (threadIdx.x < 2 * kGroups) sg[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % nvec, r0 = threadIdx.x / nvec;
+  const int rows_per_split = (HW + nsplit - 1) / nsplit;
+  const int row_begin = split * rows_per_split;
+  const int row_end = min(HW, row_begin + rows_per_split);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const uint4* base = reinterpret_cast<const uint4*>(x + static_cast<size_t>(f) * HW * C) + cv;
+  for (int r = row_begin + r0; r < row_end; r += rpi) {
+    float v[8];
+    unpack8(__ldg(base + static_cast<size_t>(r) * nvec), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += v[j];
+      q[j] += v[j] * v[j];
+    }
+  }
+  flush_groups(s, q, cv * 8, C / kGroups, sg);
+  __syncthreads();
+  if (threadIdx.x < 2 * kGroups)
+    partial[(static_cast<size_t>(f) * nsplit + split) * 2 * kGroups + threadIdx.x] = sg[threadIdx.x];
+}
+
+// spatial GroupNorm: apply (+ optional SiLU). grid (nchunk, F)
+__global__ void gn_spatial_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const float* __restrict__ partial, int HW, int C, int nvec, int rpi, int nsplit,
+                                        float eps, int silu) {
+  __shared__ float smean[kGroups], srstd[kGroups];
+  const int f = blockIdx.y;
+  if (threadIdx.x < kGroups) {
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < nsplit; ++k) {
+      const float* pp = partial + (static_cast<size_t>(f) * nsplit + k) * 2 * kGroups;
+      s += pp[2 * threadIdx.x];
+      q += pp[2 * threadIdx.x + 1];
+    }
+    const float n = static_cast<float>(HW) * static_cast<float>(C / kGroups);
+    const float mean = s / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    smean[threadIdx.x] = mean;
+    srstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int cv = threadIdx.x % nvec, r0 = threadIdx.x / nvec;
+  const int cpg = C / kGroups;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float a = srstd[g] * gamma[c];
+    sc[j] = a;
+    sh[j] = beta[c] - smean[g] * a;
+  }
+  const int rows_per_chunk = (HW + gridDim.x - 1) / gridDim.x;
+  const int row_begin = blockIdx.x * rows_per_chunk;
+  const int row_end = min(HW, row_begin + rows_per_chunk);
+  const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(f) * HW * C) + cv;
+  uint4* yb = reinterpret_cast<uint4*>(y + static_cast<size_t>(f) * HW * C) + cv;
+  for (int r = row_begin + r0; r < row_end; r += rpi) {
+    float v[8];
+    unpack8(__ldg(xb + static_cast<size_t>(r) * nvec), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j] * sc[j] + sh[j];
+      v[j] = silu ? silu_f(t) : t;
+    }
+    yb[static_cast<size_t>(r) * nvec] = pack8(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// temporal GroupNorm: one block handles `ppb` pixels; statistics over (C/32, T) per pixel.
+// x: [B][T][HW][C]; second pass re-reads the block's rows (L1/L2 resident) instead of holding T vectors in registers.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, int B, int T, int HW,
+                                   int C, int nvec, int ppb, float eps, int silu) {
+  extern __shared__ float sg_dyn[];  // [ppb][64]
+  const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+  const long long pix = static_cast<long long>(blockIdx.x) * ppb + pl;  // over B*HW
+  for (int i = threadIdx.x; i < ppb * 2 * kGroups; i += blockDim.x) sg_dyn[i] = 0.f;
+  __syncthreads();
+  const bool active = pix < static_cast<long long>(B) * HW;
+  const int b = active ? static_cast<int>(pix / HW) : 0;
+  const int hw = active ? static_cast<int>(pix % HW) : 0;
+  const size_t tstride = static_cast<size_t>(HW) * nvec;  // in uint4
+  const uint4* xb = reinterpret_cast<const uint4*>(x) + (static_cast<size_t>(b) * T * HW + hw) * nvec + cv;
+  uint4* yb = reinterpret_cast<uint4*>(y) + (static_cast<size_t>(b) * T * HW + hw) * nvec + cv;
+  const int cpg = C / kGroups;
+  float* sg = sg_dyn + pl * 2 * kGroups;
+  if (active) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      float v[8];
+      unpack8(__ldg(xb + t * tstride), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] += v[j] * v[j];
+      }
+    }
+    flush_groups(s, q, cv * 8, cpg, sg);
+  }
+  __syncthreads();
+  if (active) {
+    float sc[8], sh[8];
+    const float n = static_cast<float>(T) * static_cast<float>(cpg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cv * 8 + j;
+      const int g = c / cpg;
+      const float mean = sg[2 * g] / n;
+      const float var = fmaxf(sg[2 * g + 1] / n - mean * mean, 0.f);
+      const float a = rsqrtf(var + eps) * gamma[c];
+      sc[j] = a;
+      sh[j] = beta[c] - mean * a;
+    }
+    for (int t = 0; t < T; ++t) {
+      float v[8];
+      unpack8(__ldg(xb + t * tstride), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float u = v[j] * sc[j] + sh[j];
+        v[j] = silu ? silu_f(u) : u;
+      }
+      yb[t * tstride] = pack8(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per token row, two-pass statistics on register-resident data. C <= 32*8*kLnVecs.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kLnVecs = 10;  // up to C = 2560
+__global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int C,
+                                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+  float v[kLnVecs][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnVecs; ++i) {
+    const int iv = lane + 32 * i;
+    if (iv < nvec) {
+      unpack8(__ldg(xr + iv), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnVecs; ++i) {
+    const int iv = lane + 32 * i;
+    if (iv < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dlt = v[i][j] - mean;
+        q += dlt * dlt;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * static_cast<long long>(C));
+#pragma unroll
+  for (int i = 0; i < kLnVecs; ++i) {
+    const int iv = lane + 32 * i;
+    if (iv < nvec) {
+      const float4* g4 = reinterpret_cast<const float4*>(gamma + iv * 8);
+      const float4* b4 = reinterpret_cast<const float4*>(beta + iv * 8);
+      const float4 ga = __ldg(g4), gb = __ldg(g4 + 1), ba = __ldg(b4), bb = __ldg(b4 + 1);
+      const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + be[j];
+      yr[iv] = pack8(o);
+    }
+  }
+}
+
+static int pick_rpi(int nvec) {
+  int rpi = 256 / nvec;
+  return rpi < 1 ? 1 : rpi;
+}
+
+}  // namespace ccedit
+
+using namespace ccedit;
+
+extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gamma, const float* beta, float* partial,
+                                        int32_t F, int32_t HW, int32_t C, float eps, int32_t silu, void* stream) {
+  CCEDIT_CHECK_ARG(x && y && gamma && beta && partial, "ccedit_groupnorm_spatial: null pointer");
+  CCEDIT_CHECK_ARG(F > 0 && HW > 0 && C > 0 && C % kGroups == 0 && C % 8 == 0 && C <= 8192,
+                   "ccedit_groupnorm_spatial: bad shape F=%d HW=%d C=%d (C must be a multiple of 32)", F, HW, C);
+  const int nvec = C / 8, rpi = pick_rpi(nvec);
+  const int threads = nvec * rpi;
+  long long bytes = static_cast<long long>(HW) * C * 2;
+  int nsplit = static_cast<int>(bytes / 65536);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  gn_spatial_stats_kernel<<<dim3(nsplit, F), threads, 0, st>>>(static_cast<const __half*>(x), partial, HW, C, nvec, rpi,
+                                                               nsplit);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_spatial(stats)");
+  int nchunk = static_cast<int>(bytes / 32768);
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 64) nchunk = 64;
+  gn_spatial_apply_kernel<<<dim3(nchunk, F), threads, 0, st>>>(static_cast<const __half*>(x), static_cast<__half*>(y),
+                                                               gamma, beta, partial, HW, C, nvec, rpi, nsplit, eps, silu);
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_spatial(apply)");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_groupnorm_temporal(const void* x, void* y, const float* gamma, const float* beta, int32_t B,
+                                         int32_t T, int32_t HW, int32_t C, float eps, int32_t silu, void* stream) {
+  CCEDIT_CHECK_ARG(x && y && gamma && beta, "ccedit_groupnorm_temporal: null pointer");
+  CCEDIT_CHECK_ARG(B > 0 && T > 0 && HW > 0 && C > 0 && C % kGroups == 0 && C % 8 == 0 && C <= 8192,
+                   "ccedit_groupnorm_temporal: bad shape B=%d T=%d HW=%d C=%d", B, T, HW, C);
+  const int nvec = C / 8, ppb = pick_rpi(nvec);
+  const int threads = nvec * ppb;
+  const long long npix = static_cast<long long>(B) * HW;
+  const int grid = static_cast<int>((npix + ppb - 1) / ppb);
+  gn_temporal_kernel<<<grid, threads, ppb * 2 * kGroups * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, B, T, HW, C, nvec, ppb, eps, silu);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_temporal");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_layernorm(const void* x, int64_t ldx, void* y, const float* gamma, const float* beta, int64_t M,
+                                int32_t C, float eps, void* stream) {
+  CCEDIT_CHECK_ARG(x && y && gamma && beta, "ccedit_layernorm: null pointer");
+  CCEDIT_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0 && C <= 32 * 8 * kLnVecs && ldx % 8 == 0,
+                   "ccedit_layernorm: bad shape M=%lld C=%d ldx=%lld", (long long)M, C, (long long)ldx);
+  const int wpb = 8;
+  const long long grid = (M + wpb - 1) / wpb;
+  layernorm_kernel<<<static_cast<unsigned>(grid), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), ldx, static_cast<__half*>(y), gamma, beta, M, C, eps);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_layernorm");
+  return CCEDIT_OK;
+}

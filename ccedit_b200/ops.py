@@ -1,0 +1,439 @@
+"""Thin tensor-plumbing layer over the C-ABI kernels (include/ccedit_b200.h).
+
+Every function takes CUDA fp16 tensors in the canonical channels-last layout, derives raw pointers / strides and makes
+exactly one C-ABI call on the current CUDA stream.  PyTorch is used for memory and streams only - there is no torch
+compute and no fallback here: a missing library or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import itertools
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import AttnDesc, GemmDesc
+
+BLOCK_M = 128
+BLOCK_K = 64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require(t: torch.Tensor, dtype=torch.float16, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"ccedit_b200: {name} must be a CUDA tensor (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"ccedit_b200: {name} must be {dtype}, got {t.dtype}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------------------------------
+def pick_bn(n: int, geglu: bool = False) -> int:
+    """Largest N tile (multiple of 16, <= 256; multiple of 32 for GEGLU) that divides n."""
+    step = 32 if geglu else 16
+    for bn in range(256, 0, -step):
+        if n % bn == 0:
+            return bn
+    raise ValueError(f"output width {n} is not a multiple of {step}")
+
+
+@dataclass
+class PackedWeight:
+    """fp16 weight in the tap-GEMM layout [N][ntaps][kpad] (+ fp32 bias)."""
+
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]
+    n: int
+    k: int
+    kpad: int
+    ntaps: int
+    bn: int
+    geglu: bool = False
+
+    @property
+    def n_out(self) -> int:
+        return self.n // 2 if self.geglu else self.n
+
+
+def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor], device, geglu: bool = False, n_pad_to: int = 16,
+                cin_pad_to: int = 8) -> PackedWeight:
+    """w: [N, Cin, *taps] in the reference (PyTorch) layout: Linear [N,K], Conv2d [N,Cin,kh,kw], Conv1d [N,Cin,kt].
+
+    Tap order is row-major over the kernel dims (kh*3+kw / kt), matching ``conv_taps``/``temporal_taps``.
+    GEGLU: rows are re-ordered so that every BN tile holds BN/2 value rows followed by their BN/2 gate rows
+    (reference: value = first half of the 2*inner outputs, gate = second half; attention.py:120-122).
+    """
+    w = w.detach().to(torch.float32)
+    n, cin = w.shape[0], w.shape[1]
+    ntaps = int(math.prod(w.shape[2:])) if w.dim() > 2 else 1
+    w = w.reshape(n, cin, ntaps).permute(0, 2, 1)  # [N, taps, Cin]
+    b = None if bias is None else bias.detach().to(torch.float32)
+    n_p = ((n + n_pad_to - 1) // n_pad_to) * n_pad_to
+    if n_p != n:
+        w = torch.cat([w, w.new_zeros(n_p - n, ntaps, cin)], 0)
+        if b is not None:
+            b = torch.cat([b, b.new_zeros(n_p - n)], 0)
+    bn = pick_bn(n_p, geglu)
+    if geglu:
+        half = n_p // 2
+        hb = bn // 2
+        idx = []
+        for j in range(n_p // bn):
+            idx += list(range(j * hb, (j + 1) * hb)) + list(range(half + j * hb, half + (j + 1) * hb))
+        idx = torch.tensor(idx, dtype=torch.long)
+        w = w[idx]
+        if b is not None:
+            b = b[idx]
+    kpad = ((cin + BLOCK_K - 1) // BLOCK_K) * BLOCK_K
+    wp = w.new_zeros(n_p, ntaps, kpad)
+    wp[:, :, :cin] = w
+    wp = wp.reshape(n_p, ntaps * kpad).to(device=device, dtype=torch.float16).contiguous()
+    bp = None if b is None else b.to(device=device, dtype=torch.float32).contiguous()
+    return PackedWeight(wp, bp, n_p, cin, kpad, ntaps, bn, geglu)
+
+
+def conv_taps():
+    """3x3, stride 1, pad 1: tap (kh,kw) reads (h+kh-1, w+kw-1); offsets along (d1=W, d2=H, d3, d4)."""
+    return [(kw - 1, kh - 1, 0, 0) for kh in range(3) for kw in range(3)]
+
+
+def conv_s2_taps():
+    """3x3, stride 2, pad 1 over the 4 parity planes (d3 = plane = (h&1)*2 + (w&1)) of ``parity_split``."""
+    def split(k):  # input index 2*o + k - 1  ->  (parity, offset)
+        return (1, -1) if k == 0 else ((0, 0) if k == 1 else (1, 0))
+    taps = []
+    for kh in range(3):
+        ph, oh = split(kh)
+        for kw in range(3):
+            pw, ow = split(kw)
+            taps.append((ow, oh, ph * 2 + pw, 0))
+    return taps
+
+
+def temporal_taps(k: int = 3):
+    """Conv1d over T (d2), zero padded: tap kt reads t + kt - k//2."""
+    return [(0, kt - k // 2, 0, 0) for kt in range(k)]
+
+
+ONE_TAP = [(0, 0, 0, 0)]
+
+
+@functools.lru_cache(maxsize=None)
+def pick_box(dims: tuple) -> tuple:
+    """Tile extents (powers of two, product 128) along d1..d4 minimising padded rows; ties -> larger inner extents."""
+    best, best_cost = None, None
+    for e in itertools.product(range(8), repeat=4):
+        if sum(e) != 7:
+            continue
+        box = tuple(1 << x for x in e)
+        cost = 1
+        for o, b in zip(dims, box):
+            cost *= -(-o // b)
+        key = (cost, -box[0], -box[1], -box[2])
+        if best_cost is None or key < best_cost:
+            best, best_cost = box, key
+    return best
+
+
+def _dims_strides(t: torch.Tensor):
+    """Tensor [d4, d3, d2, d1, C] (left-padded with 1s) -> (C, (d1..d4), (s1..s4))."""
+    if t.stride(-1) != 1:
+        raise RuntimeError("ccedit_b200: channel dimension must be contiguous")
+    shape, stride = list(t.shape), list(t.stride())
+    if len(shape) > 5:
+        raise RuntimeError("ccedit_b200: at most 5 dims")
+    while len(shape) < 5:
+        stride.insert(0, stride[0] * shape[0])
+        shape.insert(0, 1)
+    # size-1 dims may carry arbitrary strides; give them the dense value so that TMA's 16-byte rule holds
+    for i in range(3, -1, -1):
+        if shape[i] == 1:
+            stride[i] = stride[i + 1] * shape[i + 1]
+    dims = shape[-2::-1]
+    strides = stride[-2::-1]
+    return shape[-1], dims, strides
+
+
+def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = ONE_TAP, *,
+         rowbias: Optional[torch.Tensor] = None, rb_dim: int = 0, rb_div: int = 1,
+         res1: Optional[torch.Tensor] = None, res2: Optional[torch.Tensor] = None, silu: bool = False,
+         box: Optional[tuple] = None) -> torch.Tensor:
+    """out[p, :] = epi( sum_tap A[p + tap, :] @ W[:, tap, :]^T ).  a/out/res*: [d4, d3, d2, d1, C] views (C contiguous)."""
+    _require(a, name="a")
+    _require(out, name="out")
+    c, adims, astr = _dims_strides(a)
+    n_out, odims, ostr = _dims_strides(out)
+    if n_out != pw.n_out:
+        raise RuntimeError(f"ccedit_b200.gemm: out has {n_out} channels, weight produces {pw.n_out}")
+    if len(taps) != pw.ntaps:
+        raise RuntimeError(f"ccedit_b200.gemm: {len(taps)} taps given, weight packed for {pw.ntaps}")
+    if c != pw.k and not (c <= pw.kpad and pw.k <= c):
+        raise RuntimeError(f"ccedit_b200.gemm: a has {c} channels, weight expects {pw.k}")
+    d = GemmDesc()
+    d.a = a.data_ptr()
+    d.a_dims[0] = c
+    for i in range(4):
+        d.a_dims[i + 1] = adims[i]
+        d.a_strides[i] = astr[i]
+        d.out_dims[i] = odims[i]
+        d.out_strides[i] = ostr[i]
+    bx = box or pick_box(tuple(odims))
+    for i in range(4):
+        d.box[i] = bx[i]
+    d.ntaps = len(taps)
+    for t, tap in enumerate(taps):
+        for i in range(4):
+            d.taps[t][i] = tap[i]
+    d.w = pw.w.data_ptr()
+    d.n = pw.n
+    d.kpad = pw.kpad
+    d.bn = pw.bn
+    d.out = out.data_ptr()
+    d.bias = _ptr(pw.bias)
+    if rowbias is not None:
+        _require(rowbias, torch.float32, "rowbias")
+        if rowbias.shape[-1] != n_out or not rowbias.is_contiguous():
+            raise RuntimeError("ccedit_b200.gemm: rowbias must be contiguous [R, n_out]")
+        d.rowbias = rowbias.data_ptr()
+        d.rb_dim = rb_dim
+        d.rb_div = rb_div
+    for name, r in (("res1", res1), ("res2", res2)):
+        if r is None:
+            continue
+        _require(r, name=name)
+        rc, rdims, rstr = _dims_strides(r)
+        if rc != n_out or list(rdims) != list(odims):
+            raise RuntimeError(f"ccedit_b200.gemm: {name} shape {tuple(r.shape)} does not match out {tuple(out.shape)}")
+        setattr(d, name, r.data_ptr())
+        arr = getattr(d, name + "_strides")
+        for i in range(4):
+            arr[i] = rstr[i]
+    d.flags = (_lib.GEMM_SILU if silu else 0) | (_lib.GEMM_GEGLU if pw.geglu else 0)
+    _lib.check(_lib.load().ccedit_gemm(C.byref(d), _stream()), "ccedit_gemm")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# normalisation
+# ---------------------------------------------------------------------------------------------------------------------
+_GN_SCRATCH = {}
+
+
+def _gn_scratch(device, F: int) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    need = F * 32 * 64
+    buf = _GN_SCRATCH.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.float32, device=device)
+        _GN_SCRATCH[key] = buf
+    return buf
+
+
+def groupnorm_spatial(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: contiguous [F, HW, C] (or [F, H, W, C]); GroupNorm(32, C) per frame (+ SiLU)."""
+    _require(x, name="x")
+    if not x.is_contiguous():
+        raise RuntimeError("ccedit_b200.groupnorm_spatial: x must be contiguous")
+    F, Cc = x.shape[0], x.shape[-1]
+    HW = x.numel() // (F * Cc)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.load().ccedit_groupnorm_spatial(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                   _gn_scratch(x.device, F).data_ptr(), F, HW, Cc, eps, int(silu),
+                                                   _stream()), "ccedit_groupnorm_spatial")
+    return out
+
+
+def groupnorm_temporal(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: contiguous [B, T, HW, C] (or [B, T, H, W, C]); GroupNorm(32, C) over (C/32, T) per pixel (+ SiLU)."""
+    _require(x, name="x")
+    if not x.is_contiguous():
+        raise RuntimeError("ccedit_b200.groupnorm_temporal: x must be contiguous")
+    B, T, Cc = x.shape[0], x.shape[1], x.shape[-1]
+    HW = x.numel() // (B * T * Cc)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.load().ccedit_groupnorm_temporal(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                    B, T, HW, Cc, eps, int(silu), _stream()),
+               "ccedit_groupnorm_temporal")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [..., C] with a uniform row stride (contiguous or a channel slice); per-row LayerNorm -> contiguous."""
+    _require(x, name="x")
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    if x.dim() == 2:
+        x2 = x
+    elif x.is_contiguous():
+        x2 = x.view(M, Cc)
+    else:
+        raise RuntimeError("ccedit_b200.layernorm: x must be 2-D (row stride free) or contiguous")
+    if x2.stride(1) != 1:
+        raise RuntimeError("ccedit_b200.layernorm: channel dimension must be contiguous")
+    ldx = x2.stride(0)
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device) if out is None else out
+    _lib.check(_lib.load().ccedit_layernorm(x2.data_ptr(), ldx, out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M,
+                                           Cc, eps, _stream()), "ccedit_layernorm")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class KVSegment:
+    """k, v: [Fkv, Lkv, heads*d] views (row stride free); query frame f reads kv frame (f // div) * mul + add."""
+
+    k: torch.Tensor
+    v: torch.Tensor
+    div: int = 1
+    mul: int = 1
+    add: int = 0
+
+
+def attention(q: torch.Tensor, segments: Sequence[KVSegment], heads: int, out: torch.Tensor,
+              scale: Optional[float] = None) -> torch.Tensor:
+    """q, out: [F, L, heads*d] views.  softmax(q k^T * scale) v over the concatenation of the key segments."""
+    _require(q, name="q")
+    _require(out, name="out")
+    F, L, Cc = q.shape
+    dh = Cc // heads
+    a = AttnDesc()
+    a.q, a.ldq, a.q_frame_stride = q.data_ptr(), q.stride(1), q.stride(0)
+    a.o, a.ldo, a.o_frame_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    a.nseg = len(segments)
+    for s, seg in enumerate(segments):
+        _require(seg.k, name="k")
+        _require(seg.v, name="v")
+        a.k[s], a.v[s] = seg.k.data_ptr(), seg.v.data_ptr()
+        a.ldk[s], a.ldv[s] = seg.k.stride(1), seg.v.stride(1)
+        if seg.k.stride(0) != seg.v.stride(0):
+            raise RuntimeError("ccedit_b200.attention: k and v must share the frame stride")
+        a.kv_frame_stride[s] = seg.k.stride(0)
+        a.lkv[s] = seg.k.shape[1]
+        a.kv_div[s], a.kv_mul[s], a.kv_add[s] = seg.div, seg.mul, seg.add
+    a.frames, a.lq, a.heads, a.d = F, L, heads, dh
+    a.scale = float(dh) ** -0.5 if scale is None else scale
+    _lib.check(_lib.load().ccedit_attention(C.byref(a), _stream()), "ccedit_attention")
+    return out
+
+
+def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, out: torch.Tensor,
+                       scale: Optional[float] = None) -> torch.Tensor:
+    """q, k, v, out: [B, T, HW, heads*d] views with uniform row stride; attention over T for every (b, pixel, head)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _require(t, name=nm)
+    B, T, HW, Cc = q.shape
+    dh = Cc // heads
+    sc = float(dh) ** -0.5 if scale is None else scale
+    _lib.check(_lib.load().ccedit_temporal_attention(q.data_ptr(), q.stride(2), k.data_ptr(), k.stride(2), v.data_ptr(),
+                                                    v.stride(2), out.data_ptr(), out.stride(2), B, T, HW, heads, dh,
+                                                    sc, _stream()), "ccedit_temporal_attention")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# small kernels
+# ---------------------------------------------------------------------------------------------------------------------
+def ncthw_to_cl(src: torch.Tensor, cpad: int, mul: float = 1.0, add: float = 0.0) -> torch.Tensor:
+    """[B, C, T, H, W] fp32/fp16 -> [B, T, H, W, cpad] fp16 (v*mul+add, zero padded channels)."""
+    if not src.is_cuda:
+        raise RuntimeError("ccedit_b200: src must be a CUDA tensor (no CPU fallback)")
+    if src.dtype not in (torch.float32, torch.float16):
+        src = src.float()
+    src = src.contiguous()
+    B, Cin, T, H, W = src.shape
+    dst = torch.empty(B, T, H, W, cpad, dtype=torch.float16, device=src.device)
+    _lib.check(_lib.load().ccedit_ncthw_to_cl(src.data_ptr(), int(src.dtype == torch.float32), dst.data_ptr(), B, Cin,
+                                             T, H, W, cpad, mul, add, _stream()), "ccedit_ncthw_to_cl")
+    return dst
+
+
+def out_temporal(y: torch.Tensor, wt: torch.Tensor, bias_t: torch.Tensor, cout: int, out_dtype) -> torch.Tensor:
+    """y: [B, T, H, W, ld] fp16 -> [B, cout, T, H, W] (y + conv1d_k3(silu(y)) over T)."""
+    _require(y, name="y")
+    B, T, H, W, ld = y.shape
+    dst = torch.empty(B, cout, T, H, W, dtype=out_dtype, device=y.device)
+    _lib.check(_lib.load().ccedit_out_temporal(y.data_ptr(), ld, wt.data_ptr(), bias_t.data_ptr(), dst.data_ptr(),
+                                              int(out_dtype == torch.float32), B, cout, T, H * W, _stream()),
+               "ccedit_out_temporal")
+    return dst
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    tf = t.to(torch.float32).contiguous()
+    out = torch.empty(tf.shape[0], dim, dtype=torch.float32, device=tf.device)
+    _lib.check(_lib.load().ccedit_timestep_embedding(tf.data_ptr(), out.data_ptr(), tf.shape[0], dim, max_period,
+                                                    _stream()), "ccedit_timestep_embedding")
+    return out
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act_in: bool = False,
+                 act_out: bool = False) -> torch.Tensor:
+    """fp32 x [M<=8, K] @ fp16 w [N, K]^T + b -> fp32 [M, N]; optional SiLU on the input and/or output."""
+    _require(x, torch.float32, "x")
+    _require(w, torch.float16, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ccedit_linear_small(x.data_ptr(), w.data_ptr(), _ptr(b), out.data_ptr(), M, N, K,
+                                              int(act_in), int(act_out), _stream()), "ccedit_linear_small")
+    return out
+
+
+def parity_split(x: torch.Tensor) -> torch.Tensor:
+    """[F, H, W, C] -> [F, 4, H/2, W/2, C]."""
+    _require(x, name="x")
+    F, H, W, Cc = x.shape
+    y = torch.empty(F, 4, H // 2, W // 2, Cc, dtype=torch.float16, device=x.device)
+    _lib.check(_lib.load().ccedit_parity_split(x.data_ptr(), y.data_ptr(), F, H, W, Cc, _stream()),
+               "ccedit_parity_split")
+    return y
+
+
+def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
+    """[F, H, W, C] -> [F, 2H, 2W, C]."""
+    _require(x, name="x")
+    F, H, W, Cc = x.shape
+    y = torch.empty(F, 2 * H, 2 * W, Cc, dtype=torch.float16, device=x.device)
+    _lib.check(_lib.load().ccedit_upsample_nearest2x(x.data_ptr(), y.data_ptr(), F, H, W, Cc, _stream()),
+               "ccedit_upsample_nearest2x")
+    return y
+
+
+def add_rows(a: torch.Tensor, b: Optional[torch.Tensor], dst: torch.Tensor) -> torch.Tensor:
+    """dst[..., :] = a + b for [M, C] views with uniform row strides (dst may be a channel slice of a wider buffer)."""
+    Cc = a.shape[-1]
+    M = a.numel() // Cc
+    a2, d2 = a.reshape(M, Cc) if a.is_contiguous() else a.view(M, Cc), dst.view(M, Cc)
+    b2 = None if b is None else (b.reshape(M, Cc) if b.is_contiguous() else b.view(M, Cc))
+    _lib.check(_lib.load().ccedit_add_rows(a2.data_ptr(), a2.stride(0), _ptr(b2), 0 if b2 is None else b2.stride(0),
+                                          d2.data_ptr(), d2.stride(0), M, Cc, _stream()), "ccedit_add_rows")
+    return dst
+
+
+def add_center_frame(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """x: [B, T, H, W, C] contiguous; y: [B, H, W, C]; x[:, T//2] += y in place."""
+    _require(x, name="x")
+    _require(y, name="y")
+    B, T = x.shape[0], x.shape[1]
+    Cc = x.shape[-1]
+    HW = x.numel() // (B * T * Cc)
+    _lib.check(_lib.load().ccedit_add_center_frame(x.data_ptr(), y.data_ptr(), B, T, HW, Cc, _stream()),
+               "ccedit_add_center_frame")
+    return x

@@ -1,0 +1,157 @@
+/*
+ * ccedit_b200 — C ABI of the B200-native (sm_100a) kernels behind CCEdit's denoising hot path.
+ *
+ * The reference (RuoyuFeng/CCEdit) is 100 % Python/PyTorch and has no FFI of its own; every entry point below
+ * replaces one family of ATen call sites inside
+ *   OpenAIWrapperControlLDM3DTV2V.forward   sgm/modules/diffusionmodules/wrappers.py:155-207
+ *   ControlNet2D.forward                    sgm/modules/diffusionmodules/controlmodel.py:252-317
+ *   ControlledUNetModel3DTV2V.forward       sgm/modules/diffusionmodules/controlmodel.py:471-550
+ * The host-side mirror of those classes (ccedit_b200/*.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless stated; no torch types.
+ *  - activations are fp16, channels-last: a video tensor is [B][T][H][W][C] (C contiguous), a token matrix [M][C].
+ *  - every function is asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 on success and a
+ *    non-zero code otherwise; ccedit_last_error() returns the message of the last failure on the calling thread.
+ *  - there is NO CPU fallback: without a CUDA device / sm_100a the calls fail with CCEDIT_ERR_CUDA.
+ */
+#ifndef CCEDIT_B200_H_
+#define CCEDIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCEDIT_OK 0
+#define CCEDIT_ERR_INVALID 1
+#define CCEDIT_ERR_CUDA 2
+
+const char* ccedit_last_error(void);
+/* ABI version of this library (bumped when a struct below changes). */
+int ccedit_abi_version(void);
+/* Number of kernels launched by this library on the calling process since load (bench.py's gpu_launches). */
+int64_t ccedit_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tap-GEMM on tcgen05 tensor cores (TMA-staged operands, TMEM accumulators).
+ *
+ *   out[p, n] = epilogue( sum_{tap} sum_{c} A[p + tap, c] * W[n, tap, c] )
+ *
+ * A is a 5-D fp16 tensor (C, d1, d2, d3, d4) with C contiguous; p ranges over the 4-D output grid out_dims[0..3]
+ * (same axes d1..d4); a tap is a 4-D integer offset; reads outside A return zero (TMA out-of-bounds fill), which is
+ * the convolution zero padding.  This one primitive is
+ *   nn.Linear / 1x1 conv / Conv1d k=1  (1 tap)             attention.py:383-388,118,136 ; openaimodel.py:706-709
+ *   3x3 conv, stride 1, pad 1          (9 taps on d1,d2)   openaimodel.py:444-448,479-492,612-616,660-673
+ *   3x3 conv, stride 2 (Downsample)    (9 taps over 4 parity planes on d3)  openaimodel.py:308-315,361-368
+ *   temporal Conv1d k=3, pad 1         (3 taps on the T axis)               openaimodel.py:617-629,674-687
+ * W is fp16 [N][ntaps][kpad] (kpad = C rounded up to 64, zero padded).
+ * Epilogue (fp32): + bias[n] + rowbias[coord[rb_dim]/rb_div][n] ; optional SiLU ; optional GEGLU (value*gelu(gate),
+ * attention.py:115-122, W rows interleaved per BN tile: BN/2 value rows then BN/2 gate rows) ; + res1 + res2 ;
+ * fp16 store at out + sum_i coord_i*out_strides[i] + n.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define CCEDIT_GEMM_SILU 1
+#define CCEDIT_GEMM_GEGLU 2
+#define CCEDIT_MAX_TAPS 9
+
+typedef struct ccedit_gemm_desc {
+  const void* a;          /* fp16 A base                                                            */
+  int32_t a_dims[5];      /* extents (C, d1, d2, d3, d4)                                            */
+  int64_t a_strides[4];   /* element strides of d1..d4 (C stride is 1); each *2 bytes % 16 == 0     */
+  int32_t box[4];         /* tile extents along d1..d4, product must be 128                         */
+  int32_t out_dims[4];    /* output grid extents along d1..d4                                       */
+  int32_t ntaps;          /* 1..9                                                                   */
+  int32_t taps[CCEDIT_MAX_TAPS][4]; /* offsets along d1..d4 added to the output coordinate          */
+  const void* w;          /* fp16 [N][ntaps*kpad]                                                   */
+  int32_t n;              /* output channels of W (GEGLU: value+gate rows, out has n/2 channels)    */
+  int32_t kpad;           /* per-tap padded K, multiple of 64, >= a_dims[0]                         */
+  int32_t bn;             /* N tile: multiple of 16, 16..256, divides n                             */
+  void* out;              /* fp16                                                                   */
+  int64_t out_strides[4]; /* element strides of d1..d4 in out (channel stride 1)                    */
+  const float* bias;      /* [n] or NULL                                                            */
+  const float* rowbias;   /* [R][n_out] or NULL                                                     */
+  int32_t rb_dim;         /* which of d1..d4 (0..3) indexes rowbias                                 */
+  int32_t rb_div;         /* rowbias row = coord[rb_dim] / rb_div                                   */
+  const void* res1;       /* fp16 or NULL                                                           */
+  int64_t res1_strides[4];
+  const void* res2;       /* fp16 or NULL                                                           */
+  int64_t res2_strides[4];
+  int32_t flags;          /* CCEDIT_GEMM_*                                                          */
+} ccedit_gemm_desc;
+
+int ccedit_gemm(const ccedit_gemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Normalisation (fp32 statistics, fp16 in/out).
+ * GroupNorm(32, C): spatial = per frame over (C/32)*HW  (util.py:296-302, attention.py:153-156; openaimodel.py:147)
+ *                   temporal = per pixel over (C/32)*T   (openaimodel.py:157)
+ * LayerNorm(C) per token (attention.py:667-669, 749-750).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* x,y: [F][HW][C]; partial: fp32 scratch [F][nsplit][32][2]; gamma/beta fp32 [C]. silu!=0 fuses SiLU. */
+int ccedit_groupnorm_spatial(const void* x, void* y, const float* gamma, const float* beta, float* partial,
+                             int32_t F, int32_t HW, int32_t C, float eps, int32_t silu, void* stream);
+/* x,y: [B][T][HW][C]; statistics over (C/32, T) for every (b, hw). */
+int ccedit_groupnorm_temporal(const void* x, void* y, const float* gamma, const float* beta, int32_t B, int32_t T,
+                              int32_t HW, int32_t C, float eps, int32_t silu, void* stream);
+/* x: [M][C] with row stride ldx (elements); y: [M][C] contiguous. */
+int ccedit_layernorm(const void* x, int64_t ldx, void* y, const float* gamma, const float* beta, int64_t M, int32_t C,
+                     float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Attention (F.scaled_dot_product_attention call site attention.py:444-448; scale = d^-1/2; 8 heads typical).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Flash-style softmax(q k^T * scale) v over up to two concatenated key/value segments.
+ * q: [Fq][Lq][*] rows of stride ldq, head h at column h*d;  o: [Fq][Lq][heads*d] with stride ldo.
+ * segment s: k,v rows [Fkv][Lkv_s] with strides ldk/ldv; query frame f reads kv frame (f / kv_div_s) * kv_mul_s + kv_add_s.
+ * d in {40, 80, 160} (C/8 of the SD-1.5 widths) or any multiple of 8 up to 160. */
+typedef struct ccedit_attn_desc {
+  const void* q; int64_t ldq; int64_t q_frame_stride;
+  void* o; int64_t ldo; int64_t o_frame_stride;
+  int32_t nseg;
+  const void* k[2]; const void* v[2];
+  int64_t ldk[2]; int64_t ldv[2]; int64_t kv_frame_stride[2];
+  int32_t lkv[2]; int32_t kv_div[2]; int32_t kv_mul[2]; int32_t kv_add[2];
+  int32_t frames; int32_t lq; int32_t heads; int32_t d;
+  float scale;
+} ccedit_attn_desc;
+int ccedit_attention(const ccedit_attn_desc* d, void* stream);
+
+/* Temporal attention: for every (b, pixel, head) attend over the T frames (attention.py:1182-1194, 758-761).
+ * q: [B][T][HW][*] row stride ldq; k, v likewise (ldk, ldv); o: [B][T][HW][heads*d] stride ldo. T <= 64. */
+int ccedit_temporal_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                              void* o, int64_t ldo, int32_t B, int32_t T, int32_t HW, int32_t heads, int32_t d,
+                              float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Small / layout kernels.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* [B][Cin][T][H][W] (fp32 if src_f32 else fp16) -> channels-last fp16 [B][T][H][W][Cpad], channels >= Cin zeroed,
+ * value = v*mul + add (the hint transform 1-(h+1)/2 of wrappers.py:160-162 is mul=-0.5, add=0.5). */
+int ccedit_ncthw_to_cl(const void* src, int32_t src_f32, void* dst, int32_t B, int32_t Cin, int32_t T, int32_t H,
+                       int32_t W, int32_t Cpad, float mul, float add, void* stream);
+/* UNet tail (controlmodel.py:550; openaimodel.py:1627-1632): y is the spatial out conv result, channels-last fp16
+ * [B][T][HW][ldy] (first Cout channels valid); dst[b][c][t][hw] = y + bias_t[c] + sum_{dt,c'} wt[c][c'][dt] *
+ * silu(y[b][t+dt-1][hw][c']) with zero padding in t; dst is fp32 if dst_f32 else fp16, layout [B][Cout][T][HW]. */
+int ccedit_out_temporal(const void* y, int32_t ldy, const float* wt, const float* bias_t, void* dst, int32_t dst_f32,
+                        int32_t B, int32_t Cout, int32_t T, int32_t HW, void* stream);
+/* Sinusoidal timestep embedding (util.py:244-268): out fp32 [B][dim] = [cos(t f_i), sin(t f_i)]. */
+int ccedit_timestep_embedding(const float* t, float* out, int32_t B, int32_t dim, float max_period, void* stream);
+/* Small-M linear in fp32 (time_embed MLP openaimodel.py:1216-1223; ResBlock emb_layers :471-477,:652-658):
+ * out[m][n] = act_out( sum_k act_in(x[m][k]) * w[n][k] + b[n] ), w fp16 [N][K], M <= 8; act: 0 none, 1 SiLU. */
+int ccedit_linear_small(const float* x, const void* w, const float* b, float* out, int32_t M, int32_t N, int32_t K,
+                        int32_t act_in, int32_t act_out, void* stream);
+/* Split [F][H][W][C] into 4 parity planes [F][4][H/2][W/2][C] (plane = (h%2)*2 + w%2) for the stride-2 conv. */
+int ccedit_parity_split(const void* x, void* y, int32_t F, int32_t H, int32_t W, int32_t C, void* stream);
+/* Nearest x2 upsample of [F][H][W][C] -> [F][2H][2W][C] (openaimodel.py:256-260). */
+int ccedit_upsample_nearest2x(const void* x, void* y, int32_t F, int32_t H, int32_t W, int32_t C, void* stream);
+/* dst[.., dst_off + c] (row stride ldd) = a[.., c] (row stride lda) + b[.., c] (ldb; b may be NULL) for c < C. */
+int ccedit_add_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void* dst, int64_t ldd, int64_t M,
+                    int32_t C, void* stream);
+/* x[b][T/2][hw][c] += y[b][hw][c]  (img_control on the centre frame, controlmodel.py:529-535). */
+int ccedit_add_center_frame(void* x, const void* y, int32_t B, int32_t T, int32_t HW, int32_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCEDIT_B200_H_ */
