@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
         ("rowbias", C.c_void_p),
         ("rb_dim", C.c_int32),
         ("rb_div", C.c_int32),
+        ("rb_ld", C.c_int32),
         ("res1", C.c_void_p),
         ("res1_strides", C.c_int64 * 4),
         ("res2", C.c_void_p),

@@ -411,7 +411,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.rowbias = d->rowbias;
   p.rb_dim = d->rowbias ? d->rb_dim : -1;
   p.rb_div = d->rb_div > 0 ? d->rb_div : 1;
-  p.n_out_total = geglu ? d->n / 2 : d->n;
+  p.n_out_total = d->rb_ld > 0 ? d->rb_ld : (geglu ? d->n / 2 : d->n);
   p.res1 = static_cast<const __half*>(d->res1);
   p.res2 = static_cast<const __half*>(d->res2);
   p.flags = d->flags;

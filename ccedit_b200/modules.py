@@ -1,0 +1,457 @@
+"""Host-side mirror of the reference's building blocks (openaimodel.py / attention.py), executed by the CUDA kernels.
+
+Every class keeps the reference's parameter names and shapes, so the reference's state-dict keys load unchanged
+(SURVEY.md Appendix D), but `forward` never runs a torch op on activations: each block is a short list of C-ABI kernel
+calls (ccedit_b200.ops) on channels-last fp16 buffers:
+
+    video tensor   [B, T, H, W, C]      (the reference's "b c t h w")
+    frame batch    [F=B*T, H, W, C]     (the reference's "(b t) c h w")     -- same memory, no copy
+    pixel batch    [B, T, HW, C]        (the reference's "(b h w) c t")     -- same memory, no copy
+
+Parameters live in the reference layout/dtype (for load_state_dict / LoRA merging); `pack()` derives the fp16
+kernel-native copies (tap-major conv weights, fused QKV / KV, GEGLU-interleaved FF-in).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import KVSegment, PackedWeight
+
+GN_EPS_RES = 1e-5    # normalization(): util.py:296-302
+GN_EPS_ATTN = 1e-6   # Normalize():     attention.py:153-156
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parameter holders (names match torch.nn.{Conv2d,Conv1d,Linear,GroupNorm,LayerNorm} so state-dict keys line up)
+# ---------------------------------------------------------------------------------------------------------------------
+class ParamHolder(nn.Module):
+    """weight (+ bias) with the reference's shape and default init; `zero=True` mirrors zero_module()."""
+
+    def __init__(self, shape, bias=True, zero=False, norm=False):
+        super().__init__()
+        w = torch.empty(*shape)
+        if norm:
+            nn.init.ones_(w)
+        elif zero:
+            nn.init.zeros_(w)
+        else:
+            nn.init.kaiming_uniform_(w.view(shape[0], -1), a=math.sqrt(5))
+        self.weight = nn.Parameter(w)
+        if bias:
+            b = torch.zeros(shape[0])
+            if not (norm or zero):
+                bound = 1.0 / math.sqrt(max(1, math.prod(shape[1:])))
+                nn.init.uniform_(b, -bound, bound)
+            self.bias = nn.Parameter(b)
+        else:
+            self.register_parameter("bias", None)
+        self._cache = None
+
+    def forward(self, *a, **k):  # never used for compute
+        raise RuntimeError("ccedit_b200 parameter holders are not callable; use the owning block's forward")
+
+    # ---- packed views -------------------------------------------------------------------------------------------
+    def packed(self, device, geglu=False) -> PackedWeight:
+        c = self._cache
+        if c is None or c[0] != (device, "w", geglu):
+            self._cache = c = ((device, "w", geglu), ops.pack_weight(self.weight, self.bias, device, geglu=geglu))
+        return c[1]
+
+    def affine(self, device):
+        c = self._cache
+        if c is None or c[0] != (device, "affine"):
+            self._cache = c = ((device, "affine"), (
+                self.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
+                self.bias.detach().to(device=device, dtype=torch.float32).contiguous()))
+        return c[1]
+
+    def invalidate(self):
+        self._cache = None
+
+
+def conv2d(cin, cout, k, zero=False):
+    return ParamHolder((cout, cin, k, k), zero=zero)
+
+
+def conv1d(cin, cout, k, zero=False):
+    return ParamHolder((cout, cin, k), zero=zero)
+
+
+def linear(cin, cout, bias=True, zero=False):
+    return ParamHolder((cout, cin), bias=bias, zero=zero)
+
+
+def norm(c):
+    return ParamHolder((c,), norm=True)
+
+
+def seq(**mods):
+    """nn.ModuleDict keyed by the index the layer has inside the reference's nn.Sequential."""
+    return nn.ModuleDict({k.lstrip("_"): v for k, v in mods.items()})
+
+
+def _fused(device, holders: List[ParamHolder], geglu=False) -> PackedWeight:
+    """Pack the row-concatenation of several bias-free projections (QKV / KV) as one weight."""
+    w = torch.cat([h.weight.detach().float() for h in holders], 0)
+    return ops.pack_weight(w, None, device, geglu=geglu)
+
+
+def _new(ref: torch.Tensor, *shape):
+    return torch.empty(*shape, dtype=torch.float16, device=ref.device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# per-call context
+# ---------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """What a block needs beyond its input: batch geometry, per-block time-embedding rows, text K/V."""
+
+    def __init__(self, B, T, device):
+        self.B, self.T, self.device = B, T, device
+        self.emb_rows = {}   # id(resblock) -> fp32 [B, Cout] view
+        self.text_kv = {}    # id(CrossAttention) -> (k [B,77,C] view, v view)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# attention.py mirrors
+# ---------------------------------------------------------------------------------------------------------------------
+class CrossAttention(nn.Module):
+    """attention.py:365-467. to_q/to_k/to_v without bias, to_out.0 with bias; SDPA with scale d^-1/2."""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64):
+        super().__init__()
+        inner = heads * dim_head
+        context_dim = query_dim if context_dim is None else context_dim
+        self.heads, self.dim_head, self.inner = heads, dim_head, inner
+        self.to_q = linear(query_dim, inner, bias=False)
+        self.to_k = linear(context_dim, inner, bias=False)
+        self.to_v = linear(context_dim, inner, bias=False)
+        self.to_out = seq(_0=linear(inner, query_dim))
+        self._pk = {}
+
+    def fused(self, device, which):
+        key = (device, which)
+        if key not in self._pk:
+            hs = {"qkv": [self.to_q, self.to_k, self.to_v], "kv": [self.to_k, self.to_v]}[which]
+            self._pk[key] = _fused(device, hs)
+        return self._pk[key]
+
+    def invalidate(self):
+        self._pk = {}
+
+
+class FeedForward(nn.Module):
+    """attention.py:125-141 with GEGLU (:115-122): net.0.proj [8C, C], net.2 [C, 4C]."""
+
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        inner = dim * mult
+        self.net = seq(_0=nn.ModuleDict({"proj": linear(dim, inner * 2)}), _2=linear(inner, dim))
+
+    def run(self, xn, res, out=None):
+        dev = xn.device
+        g = ops.gemm(xn, self.net["0"]["proj"].packed(dev, geglu=True), _new(xn, xn.shape[0], self.net["2"].weight.shape[1]))
+        out = _new(xn, *res.shape) if out is None else out
+        return ops.gemm(g, self.net["2"].packed(dev), out, res1=res)
+
+
+class BasicTransformerBlock(nn.Module):
+    """attention.py:598-716: x += attn1(LN1 x); x += attn2(LN2 x, text); x += FF(LN3 x).  Tokens: [F*HW, C]."""
+
+    def __init__(self, dim, n_heads, d_head, context_dim):
+        super().__init__()
+        self.attn1 = CrossAttention(dim, None, n_heads, d_head)
+        self.ff = FeedForward(dim)
+        self.attn2 = CrossAttention(dim, context_dim, n_heads, d_head)
+        self.norm1, self.norm2, self.norm3 = norm(dim), norm(dim), norm(dim)
+
+    def run(self, x, F, L, ctx: Ctx):
+        dev, C, M = x.device, x.shape[1], x.shape[0]
+        heads = self.attn1.heads
+        n1 = ops.layernorm(x, *self.norm1.affine(dev))
+        qkv = ops.gemm(n1, self.attn1.fused(dev, "qkv"), _new(x, M, 3 * C))
+        q3 = qkv.view(F, L, 3 * C)
+        att = ops.attention(q3[..., :C], [KVSegment(q3[..., C:2 * C], q3[..., 2 * C:])], heads, _new(x, F, L, C))
+        x = ops.gemm(att.view(M, C), self.attn1.to_out["0"].packed(dev), _new(x, M, C), res1=x)
+        n2 = ops.layernorm(x, *self.norm2.affine(dev))
+        q = ops.gemm(n2, self.attn2.to_q.packed(dev), _new(x, M, C))
+        k, v = ctx.text_kv[id(self.attn2)]
+        att = ops.attention(q.view(F, L, C), [KVSegment(k, v, div=ctx.T)], heads, att)
+        x = ops.gemm(att.view(M, C), self.attn2.to_out["0"].packed(dev), _new(x, M, C), res1=x)
+        n3 = ops.layernorm(x, *self.norm3.affine(dev), out=n2)
+        return self.ff.run(n3, x)
+
+
+class BasicTransformerSingleLayerBlock(nn.Module):
+    """attention.py:719-761: x += attn1(LN1 x, context); x += FF(LN2 x).  K/V come from the UN-normalised context."""
+
+    def __init__(self, dim, n_heads, d_head):
+        super().__init__()
+        self.attn1 = CrossAttention(dim, None, n_heads, d_head)
+        self.ff = FeedForward(dim)
+        self.norm1, self.norm2 = norm(dim), norm(dim)
+
+    def run(self, x, attend, out=None):
+        """x: tokens [M, C]; attend(q [M,C], kv [M,2C]) -> [M, C] runs the attention of the calling layer."""
+        dev, C, M = x.device, x.shape[1], x.shape[0]
+        n1 = ops.layernorm(x, *self.norm1.affine(dev))
+        q = ops.gemm(n1, self.attn1.to_q.packed(dev), _new(x, M, C))
+        kv = ops.gemm(x, self.attn1.fused(dev, "kv"), _new(x, M, 2 * C))
+        att = attend(q, kv)
+        x = ops.gemm(att, self.attn1.to_out["0"].packed(dev), _new(x, M, C), res1=x)
+        n2 = ops.layernorm(x, *self.norm2.affine(dev), out=n1)
+        return self.ff.run(n2, x, out)
+
+
+class SpatialTransformer(nn.Module):
+    """attention.py:764-889 (2-D, depth 1, 1x1-conv projections). Input/outputs: [F, H, W, C]."""
+
+    def __init__(self, in_channels, n_heads, d_head, context_dim=None, disable_text_ca=False, **_):
+        super().__init__()
+        inner = n_heads * d_head
+        self.heads = n_heads
+        self.disable_text_ca = disable_text_ca
+        self.norm = norm(in_channels)
+        self.proj_in = conv2d(in_channels, inner, 1)
+        blk = (BasicTransformerSingleLayerBlock(inner, n_heads, d_head) if disable_text_ca
+               else BasicTransformerBlock(inner, n_heads, d_head, context_dim))
+        self.transformer_blocks = nn.ModuleList([blk])
+        self.proj_out = conv2d(inner, in_channels, 1, zero=True)
+
+    def text_attns(self):
+        return [] if self.disable_text_ca else [self.transformer_blocks[0].attn2]
+
+    def run_spatial(self, x4, ctx: Ctx, out=None):
+        """x4: [F, H, W, C] (contiguous). Returns x + proj_out(block(proj_in(GN(x)))) as [F, H, W, C]."""
+        dev = x4.device
+        F, H, W, C = x4.shape
+        L, M = H * W, F * H * W
+        xn = ops.groupnorm_spatial(x4, *self.norm.affine(dev), GN_EPS_ATTN, False)
+        h = ops.gemm(xn.view(M, C), self.proj_in.packed(dev), _new(x4, M, C))
+        blk = self.transformer_blocks[0]
+        if self.disable_text_ca:
+            def attend(q, kv):
+                kv3 = kv.view(F, L, 2 * C)
+                return ops.attention(q.view(F, L, C), [KVSegment(kv3[..., :C], kv3[..., C:])], self.heads,
+                                     _new(q, F, L, C)).view(M, C)
+            h = blk.run(h, attend)
+        else:
+            h = blk.run(h, F, L, ctx)
+        out = _new(x4, F, H, W, C) if out is None else out
+        ops.gemm(h, self.proj_out.packed(dev), out.view(M, C) if out.is_contiguous() else out.flatten(0, 2),
+                 res1=x4.view(M, C))
+        return out
+
+    def run(self, x4, ctx: Ctx, out=None):
+        return self.run_spatial(x4, ctx, out)
+
+
+class SpatialTransformer3D(SpatialTransformer):
+    """attention.py:1000-1208 (+ SpatialTransformer3DCA :1211-1350 when ca_type is set). [B, T, H, W, C] in/out."""
+
+    def __init__(self, in_channels, n_heads, d_head, context_dim=None, ca_type: Optional[str] = None, **_):
+        super().__init__(in_channels, n_heads, d_head, context_dim)
+        inner = n_heads * d_head
+        self.norm_temporal = norm(in_channels)
+        self.proj_in_temporal = conv1d(in_channels, inner, 1, zero=True)
+        self.transformer_blocks_temporal = nn.ModuleList([BasicTransformerSingleLayerBlock(inner, n_heads, d_head)])
+        self.proj_out_temporal = conv1d(inner, in_channels, 1, zero=True)
+        self.ca_type = ca_type
+        if ca_type is not None:
+            assert ca_type in ("center", "self", "center_self")
+            self.norm_temporal_ca = norm(in_channels)
+            self.proj_in_temporal_ca = conv2d(in_channels, inner, 1)
+            self.transformer_blocks_temporal_ca = nn.ModuleList([BasicTransformerSingleLayerBlock(inner, n_heads, d_head)])
+            self.proj_out_temporal_ca = conv2d(inner, in_channels, 1, zero=True)
+
+    def run(self, x5, ctx: Ctx, out=None):
+        dev = x5.device
+        B, T, H, W, C = x5.shape
+        F, L, M = B * T, H * W, B * T * H * W
+        heads = self.heads
+        xs = self.run_spatial(x5.view(F, H, W, C), ctx)                     # [F,H,W,C]
+        # ---- temporal attention over T per pixel (attention.py:1172-1207) ----
+        xt = ops.groupnorm_temporal(xs.view(B, T, L, C), *self.norm_temporal.affine(dev), GN_EPS_ATTN, False)
+        p = ops.gemm(xt.view(M, C), self.proj_in_temporal.packed(dev), _new(x5, M, C))
+
+        def attend_t(q, kv):
+            kv4 = kv.view(B, T, L, 2 * C)
+            return ops.temporal_attention(q.view(B, T, L, C), kv4[..., :C], kv4[..., C:], heads,
+                                          _new(q, B, T, L, C)).view(M, C)
+
+        p = self.transformer_blocks_temporal[0].run(p, attend_t)
+        last = self.ca_type is None
+        dst = (_new(x5, M, C) if out is None else _as2d(out, M, C)) if last else _new(x5, M, C)
+        ops.gemm(p, self.proj_out_temporal.packed(dev), dst, res1=xs.view(M, C))
+        if last:
+            return dst.view(B, T, H, W, C) if out is None else out
+        # ---- cross-frame attention (SpatialTransformer3DCA.forward, attention.py:1302-1350) ----
+        x2 = dst                                                               # [M, C] contiguous
+        xc = ops.groupnorm_spatial(x2.view(F, L, C), *self.norm_temporal_ca.affine(dev), GN_EPS_ATTN, False)
+        p = ops.gemm(xc.view(M, C), self.proj_in_temporal_ca.packed(dev), _new(x5, M, C))
+
+        def attend_ca(q, kv):
+            kv3 = kv.view(F, L, 2 * C)
+            k, v = kv3[..., :C], kv3[..., C:]
+            center = KVSegment(k, v, div=T, mul=T, add=T // 2)
+            own = KVSegment(k, v)
+            segs = {"center": [center], "self": [own], "center_self": [center, own]}[self.ca_type]
+            return ops.attention(q.view(F, L, C), segs, heads, _new(q, F, L, C)).view(M, C)
+
+        p = self.transformer_blocks_temporal_ca[0].run(p, attend_ca)
+        dst = _new(x5, M, C) if out is None else _as2d(out, M, C)
+        ops.gemm(p, self.proj_out_temporal_ca.packed(dev), dst, res1=x2)
+        return dst.view(B, T, H, W, C) if out is None else out
+
+
+def _as2d(t: torch.Tensor, M: int, C: int) -> torch.Tensor:
+    """[.., C] view with collapsible leading dims (contiguous, or a channel slice of a contiguous buffer) -> [M, C]."""
+    if t.dim() == 2:
+        return t
+    return t.as_strided((M, C), (t.stride(-2), 1), t.storage_offset())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# openaimodel.py mirrors
+# ---------------------------------------------------------------------------------------------------------------------
+class ResBlock(nn.Module):
+    """openaimodel.py:397-554 (2-D; ControlNet2D). [F, H, W, C] in/out."""
+
+    def __init__(self, channels, emb_channels, out_channels):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels
+        self.in_layers = seq(_0=norm(channels), _2=conv2d(channels, out_channels, 3))
+        self.emb_layers = seq(_1=linear(emb_channels, out_channels))
+        self.out_layers = seq(_0=norm(out_channels), _3=conv2d(out_channels, out_channels, 3, zero=True))
+        if out_channels != channels:
+            self.skip_connection = conv2d(channels, out_channels, 1)
+        else:
+            self.skip_connection = nn.Identity()
+
+    def run(self, x4, ctx: Ctx, out=None):
+        dev = x4.device
+        F, H, W, Cin = x4.shape
+        Co = self.out_channels
+        taps = ops.conv_taps()
+        a = ops.groupnorm_spatial(x4, *self.in_layers["0"].affine(dev), GN_EPS_RES, True)
+        h = ops.gemm(a, self.in_layers["2"].packed(dev), _new(x4, F, H, W, Co), taps,
+                     rowbias=ctx.emb_rows[id(self)], rb_dim=2, rb_div=ctx.T)
+        a = ops.groupnorm_spatial(h, *self.out_layers["0"].affine(dev), GN_EPS_RES, True, out=a if Co == Cin else None)
+        if isinstance(self.skip_connection, ParamHolder):
+            skip = ops.gemm(x4, self.skip_connection.packed(dev), _new(x4, F, H, W, Co))
+        else:
+            skip = x4
+        out = h if out is None else out   # h is dead after the GN above: reuse its buffer
+        return ops.gemm(a, self.out_layers["3"].packed(dev), out, taps, res1=skip)
+
+
+class ResBlock3D(ResBlock):
+    """openaimodel.py:557-775 (pseudo-3D). [B, T, H, W, C] in/out; every spatial conv is followed by
+    `y + conv1d_k3(SiLU(GN_t(y)))` along T (spatial_temporal_forward, :129-178)."""
+
+    def __init__(self, channels, emb_channels, out_channels):
+        super().__init__(channels, emb_channels, out_channels)
+        Co = out_channels
+        self.in_layers_temporal = seq(_0=norm(Co), _2=conv1d(Co, Co, 3, zero=True))
+        self.out_layers_temporal = seq(_0=norm(Co), _3=conv1d(Co, Co, 3, zero=True))
+        if out_channels != channels:
+            self.skip_connection_temporal = conv1d(Co, Co, 1, zero=True)
+        else:
+            self.skip_connection_temporal = None
+
+    def run(self, x5, ctx: Ctx, out=None):
+        dev = x5.device
+        B, T, H, W, Cin = x5.shape
+        F, L, Co = B * T, H * W, self.out_channels
+        taps, ttaps = ops.conv_taps(), ops.temporal_taps(3)
+        x4 = x5.view(F, H, W, Cin)
+        a = ops.groupnorm_spatial(x4, *self.in_layers["0"].affine(dev), GN_EPS_RES, True)
+        y = ops.gemm(a, self.in_layers["2"].packed(dev), _new(x5, F, H, W, Co), taps)
+        at = ops.groupnorm_temporal(y.view(B, T, L, Co), *self.in_layers_temporal["0"].affine(dev), GN_EPS_RES, True)
+        h = ops.gemm(at, self.in_layers_temporal["2"].packed(dev), _new(x5, B, T, L, Co), ttaps, res1=y.view(B, T, L, Co),
+                     rowbias=ctx.emb_rows[id(self)], rb_dim=2, rb_div=1)
+        a = ops.groupnorm_spatial(h.view(F, L, Co), *self.out_layers["0"].affine(dev), GN_EPS_RES, True,
+                                  out=at.view(F, L, Co))
+        y = ops.gemm(a.view(F, H, W, Co), self.out_layers["3"].packed(dev), y, taps)
+        at = ops.groupnorm_temporal(y.view(B, T, L, Co), *self.out_layers_temporal["0"].affine(dev), GN_EPS_RES, True,
+                                    out=a.view(B, T, L, Co))
+        if self.skip_connection_temporal is not None:
+            s = ops.gemm(x4, self.skip_connection.packed(dev), h.view(F, H, W, Co))      # h is dead: reuse
+            skip = ops.gemm(s.view(B, T, L, Co), self.skip_connection_temporal.packed(dev), _new(x5, B, T, L, Co),
+                            res1=s.view(B, T, L, Co))
+        else:
+            skip = x5.view(B, T, L, Co)
+        if out is None:
+            dst = _new(x5, B, T, L, Co)
+        else:
+            dst = out.view(B, T, L, Co) if out.is_contiguous() else out.flatten(2, 3)
+        ops.gemm(at, self.out_layers_temporal["3"].packed(dev), dst, ttaps, res1=y.view(B, T, L, Co), res2=skip)
+        return dst.view(B, T, H, W, Co) if out is None else out
+
+
+class Downsample(nn.Module):
+    """openaimodel.py:282-322: conv 3x3, stride 2, pad 1. [F, H, W, C] -> [F, H/2, W/2, C]."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.channels = channels
+        self.op = conv2d(channels, channels, 3)
+
+    def run(self, x4, ctx: Ctx, out=None):
+        F, H, W, C = x4.shape
+        planes = ops.parity_split(x4)
+        out = _new(x4, F, H // 2, W // 2, C) if out is None else out
+        ops.gemm(planes, self.op.packed(x4.device), out.unsqueeze(1), ops.conv_s2_taps())
+        return out
+
+
+class Downsample3D(Downsample):
+    """openaimodel.py:325-394: y = conv_s2(x) per frame; out = y + conv1d_k3(y) along T."""
+
+    def __init__(self, channels):
+        super().__init__(channels)
+        self.conv_temporal = conv1d(channels, channels, 3, zero=True)
+
+    def run(self, x5, ctx: Ctx, out=None):
+        B, T, H, W, C = x5.shape
+        y = super().run(x5.view(B * T, H, W, C), ctx)
+        L = (H // 2) * (W // 2)
+        dst = _new(x5, B, T, L, C) if out is None else (out.view(B, T, L, C) if out.is_contiguous() else out.flatten(2, 3))
+        ops.gemm(y.view(B, T, L, C), self.conv_temporal.packed(x5.device), dst, ops.temporal_taps(3),
+                 res1=y.view(B, T, L, C))
+        return dst.view(B, T, H // 2, W // 2, C) if out is None else out
+
+
+class Upsample3D(nn.Module):
+    """openaimodel.py:220-263: nearest x2 on (H, W), conv 3x3, then y + conv1d_k3(y) along T."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.channels = channels
+        self.conv = conv2d(channels, channels, 3)
+        self.conv_temporal = conv1d(channels, channels, 3, zero=True)
+
+    def run(self, x5, ctx: Ctx, out=None):
+        B, T, H, W, C = x5.shape
+        F, L = B * T, 4 * H * W
+        u = ops.upsample_nearest2x(x5.view(F, H, W, C))
+        y = ops.gemm(u, self.conv.packed(x5.device), _new(x5, F, 2 * H, 2 * W, C), ops.conv_taps())
+        dst = _new(x5, B, T, L, C) if out is None else (out.view(B, T, L, C) if out.is_contiguous() else out.flatten(2, 3))
+        ops.gemm(y.view(B, T, L, C), self.conv_temporal.packed(x5.device), dst, ops.temporal_taps(3),
+                 res1=y.view(B, T, L, C))
+        return dst.view(B, T, 2 * H, 2 * W, C) if out is None else out
+
+
+class TimestepEmbedSequential(nn.ModuleList):
+    """openaimodel.py:85-126: children are applied in order; here every child implements run(x, ctx, out)."""
+
+    def run(self, x, ctx: Ctx, out=None):
+        n = len(self)
+        for i, layer in enumerate(self):
+            x = layer.run(x, ctx, out if i == n - 1 else None)
+        return x

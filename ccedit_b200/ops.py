@@ -204,9 +204,10 @@ def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = 
     d.bias = _ptr(pw.bias)
     if rowbias is not None:
         _require(rowbias, torch.float32, "rowbias")
-        if rowbias.shape[-1] != n_out or not rowbias.is_contiguous():
-            raise RuntimeError("ccedit_b200.gemm: rowbias must be contiguous [R, n_out]")
+        if rowbias.dim() != 2 or rowbias.shape[-1] != n_out or rowbias.stride(1) != 1:
+            raise RuntimeError("ccedit_b200.gemm: rowbias must be [R, n_out] with contiguous rows")
         d.rowbias = rowbias.data_ptr()
+        d.rb_ld = rowbias.stride(0)
         d.rb_dim = rb_dim
         d.rb_div = rb_div
     for name, r in (("res1", res1), ("res2", res2)):

@@ -70,9 +70,10 @@ typedef struct ccedit_gemm_desc {
   void* out;              /* fp16                                                                   */
   int64_t out_strides[4]; /* element strides of d1..d4 in out (channel stride 1)                    */
   const float* bias;      /* [n] or NULL                                                            */
-  const float* rowbias;   /* [R][n_out] or NULL                                                     */
+  const float* rowbias;   /* [R][rb_ld] or NULL                                                     */
   int32_t rb_dim;         /* which of d1..d4 (0..3) indexes rowbias                                 */
   int32_t rb_div;         /* rowbias row = coord[rb_dim] / rb_div                                   */
+  int32_t rb_ld;          /* rowbias row stride in floats (0 => n_out)                              */
   const void* res1;       /* fp16 or NULL                                                           */
   int64_t res1_strides[4];
   const void* res2;       /* fp16 or NULL                                                           */

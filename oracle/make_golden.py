@@ -1,0 +1,163 @@
+"""ORACLE TOOLING (not product code): generate tests/golden/ from the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only:  python -m oracle.make_golden
+Writes   tests/golden/manifest_{tv2v,tvi2v}.json   state-dict key -> [shape, init kind] of the reference networks
+         tests/golden/blocks_tv2v.pt, blocks_tvi2v.pt   per-block inputs/outputs (real widths, tiny spatial sizes)
+         tests/golden/network_{tv2v,tvi2v}.pt           whole network call outputs (+ input checksums)
+         tests/golden/config1_tv2v.pt                   BASELINE config 1: B=1, T=1, 64x64 latent
+         tests/golden/sampler_tv2v.pt                   3-step DPM++2S-ancestral + CFG through the reference sampler
+Everything the reference computes here goes through its own classes; the oracle restatement is NOT involved.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import inputs as oin  # noqa: E402
+from oracle import ref_import  # noqa: E402
+from oracle.weights import GOLDEN_DIR, seeded_state_dict  # noqa: E402
+
+
+def manifest_of(module):
+    man = {}
+    for k, v in module.state_dict().items():
+        if v.numel() and bool((v == 0).all()):
+            init = "zeros"
+        elif v.numel() and bool((v == 1).all()):
+            init = "ones"
+        else:
+            init = "default"
+        man[k] = [list(v.shape), init]
+    return man
+
+
+def rnd(*shape, seed):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def run(kind):
+    t0 = time.time()
+    wrap = ref_import.build_reference_network(kind)
+    man = manifest_of(wrap)
+    with open(os.path.join(GOLDEN_DIR, f"manifest_{kind}.json"), "w") as f:
+        json.dump(man, f)
+    sd = seeded_state_dict(man, seed=0)
+    wrap.load_state_dict(sd, strict=True)
+    net = wrap.diffusion_model
+    cn = net.controlnet
+    print(kind, "built + loaded", len(man), "tensors in", round(time.time() - t0, 1), "s", flush=True)
+    blocks = {}
+    with torch.no_grad():
+        emb1, emb2 = rnd(1, 1280, seed=11), rnd(2, 1280, seed=12)
+        ctx2 = rnd(2, 77, 768, seed=13)
+
+        def rec(name, mod, args, prefix):
+            out = mod(*args)
+            blocks[name] = dict(prefix=prefix, inputs=[a.clone() for a in args], output=out.clone())
+
+        if kind == "tv2v":
+            rec("rb3d_same", net.input_blocks[1][0], (rnd(1, 320, 3, 4, 6, seed=21), emb1), "diffusion_model.input_blocks.1.0")
+            rec("rb3d_skip", net.input_blocks[4][0], (rnd(2, 320, 2, 4, 6, seed=22), emb2), "diffusion_model.input_blocks.4.0")
+            rec("rb3d_cat", net.output_blocks[11][0], (rnd(1, 640, 3, 4, 6, seed=23), emb1), "diffusion_model.output_blocks.11.0")
+            rec("st3d_320", net.input_blocks[1][1], (rnd(2, 320, 3, 4, 6, seed=24), ctx2), "diffusion_model.input_blocks.1.1")
+            rec("st3d_1280", net.input_blocks[7][1], (rnd(2, 1280, 2, 4, 4, seed=25), ctx2), "diffusion_model.input_blocks.7.1")
+            rec("down3d", net.input_blocks[3][0], (rnd(1, 320, 3, 8, 8, seed=26),), "diffusion_model.input_blocks.3.0")
+            rec("up3d", net.output_blocks[2][1], (rnd(1, 1280, 2, 3, 4, seed=27),), "diffusion_model.output_blocks.2.1")
+            rec("rb2d_skip", cn.input_blocks[4][0], (rnd(2, 320, 4, 6, seed=28), emb2), "diffusion_model.controlnet.input_blocks.4.0")
+            rec("st2d_640", cn.input_blocks[4][1], (rnd(2, 640, 4, 6, seed=29), ctx2), "diffusion_model.controlnet.input_blocks.4.1")
+            rec("down2d", cn.input_blocks[3][0], (rnd(2, 320, 8, 8, seed=30),), "diffusion_model.controlnet.input_blocks.3.0")
+            hint = torch.rand(2, 3, 32, 48, generator=torch.Generator().manual_seed(31))
+            out = cn.input_hint_block(hint, emb2, ctx2)
+            blocks["hint_block"] = dict(prefix="diffusion_model.controlnet.input_hint_block", inputs=[hint], output=out.clone())
+            # whole ControlNet2D on a video batch
+            x = rnd(1, 4, 2, 16, 16, seed=32)
+            hint5 = torch.rand(1, 3, 2, 128, 128, generator=torch.Generator().manual_seed(33))
+            t = torch.tensor([417])
+            ctx1 = rnd(1, 77, 768, seed=34)
+            outs = cn(x=x, hint=hint5, timesteps=t, context=ctx1)
+            blocks["controlnet2d"] = dict(prefix="diffusion_model.controlnet.", inputs=[x, hint5, t, ctx1],
+                                          output=[o.clone() for o in outs])
+            # UNet without control
+            out = net(x, timesteps=t, context=ctx1, control=None, img_control=None)
+            blocks["unet_nocontrol"] = dict(prefix="diffusion_model.", inputs=[x, t, ctx1], output=out.clone())
+        else:
+            rec("st3dca_320", net.input_blocks[1][1], (rnd(2, 320, 3, 4, 6, seed=41), ctx2), "diffusion_model.input_blocks.1.1")
+            rec("st3dca_1280", net.input_blocks[7][1], (rnd(1, 1280, 3, 2, 4, seed=42), ctx2[:1]), "diffusion_model.input_blocks.7.1")
+            cni = net.controlnet_img
+            rec("st2d_notext", cni.input_blocks[1][1], (rnd(2, 320, 4, 6, seed=43), ctx2), "diffusion_model.controlnet_img.input_blocks.1.1")
+            x4 = rnd(2, 4, 16, 16, seed=44)
+            feat = rnd(2, 4, 16, 16, seed=45)
+            t = torch.tensor([900, 33])
+            outs = cni(x=x4, hint=feat, timesteps=t, context=ctx2)
+            blocks["controlnet_img"] = dict(prefix="diffusion_model.controlnet_img.", inputs=[x4, feat, t, ctx2],
+                                            output=[o.clone() for o in outs])
+        torch.save(blocks, os.path.join(GOLDEN_DIR, f"blocks_{kind}.pt"))
+        print(kind, "blocks done", round(time.time() - t0, 1), "s", flush=True)
+
+        # whole network call at CFG batch 2 (B=1), T=3, 16x16 latent
+        B, T, h, w = 1, 3, 16, 16
+        c, uc = oin.synthetic_cond(B, T, h, w, seed=3, tvi2v=(kind == "tvi2v"))
+        x0 = oin.synthetic_latent(B, T, h, w, seed=2)
+        xin, tin, cc = oin.cfg_batch(x0, torch.tensor([640]), c, uc)
+        out = wrap(xin, tin, cc)
+        torch.save(dict(shape=(B, T, h, w), t=640, x_checksum=oin.checksum(xin),
+                        hint_checksum=oin.checksum(cc["control_hint"]), ctx_checksum=oin.checksum(cc["crossattn"]),
+                        output=out.clone()), os.path.join(GOLDEN_DIR, f"network_{kind}.pt"))
+        print(kind, "network done", round(time.time() - t0, 1), "s", flush=True)
+
+        if kind == "tv2v":
+            # BASELINE config 1: single UNet forward, 1 keyframe, 64x64 latent, fp32 CPU, no CFG
+            B, T, h, w = 1, 1, 64, 64
+            c, _ = oin.synthetic_cond(B, T, h, w, seed=5)
+            x0 = oin.synthetic_latent(B, T, h, w, seed=4)
+            t1 = time.time()
+            out = wrap(x0, torch.tensor([500]), c)
+            dt = time.time() - t1
+            torch.save(dict(shape=(B, T, h, w), t=500, x_checksum=oin.checksum(x0),
+                            hint_checksum=oin.checksum(c["control_hint"]), output=out.clone(), ref_seconds=dt,
+                            threads=torch.get_num_threads()), os.path.join(GOLDEN_DIR, "config1_tv2v.pt"))
+            print("config1 done: reference CPU call took", round(dt, 2), "s", flush=True)
+
+            # sampler: DiscreteDenoiser + VanillaCFGTV2V + DPMPP2SAncestralSampler, 3 steps, pre-drawn noise
+            from sgm.modules.diffusionmodules.denoiser import DiscreteDenoiser
+            from sgm.modules.diffusionmodules.sampling import DPMPP2SAncestralSampler
+
+            P = "sgm.modules.diffusionmodules."
+            den = DiscreteDenoiser(weighting_config={"target": P + "denoiser_weighting.EpsWeighting"},
+                                   scaling_config={"target": P + "denoiser_scaling.EpsScaling"}, num_idx=1000,
+                                   discretization_config={"target": P + "discretizer.LegacyDDPMDiscretization"})
+            steps, scale = 3, 7.5
+            sampler = DPMPP2SAncestralSampler(
+                num_steps=steps, discretization_config={"target": P + "discretizer.LegacyDDPMDiscretization"},
+                guider_config={"target": P + "guiders.VanillaCFGTV2V", "params": {"scale": scale}}, eta=1.0,
+                s_noise=1.0, verbose=False, device="cpu")
+            B, T, h, w = 1, 2, 16, 16
+            c, uc = oin.synthetic_cond(B, T, h, w, seed=7)
+            x0 = oin.synthetic_latent(B, T, h, w, seed=6)
+            gn = torch.Generator().manual_seed(8)
+            noises = [torch.randn(x0.shape, generator=gn) for _ in range(steps)]
+            it = iter(noises)
+            sampler.noise_sampler = lambda x: next(it)
+            calls = []
+
+            def denoiser(inp, sigma, cond):
+                calls.append(sigma.clone())
+                return den(wrap, inp, sigma, cond)
+
+            out = sampler(denoiser, x0.clone(), c, uc=uc)
+            torch.save(dict(shape=(B, T, h, w), steps=steps, scale=scale, output=out.clone(), n_calls=len(calls),
+                            call_sigmas=torch.stack([s[0] for s in calls]), denoiser_sigmas=den.sigmas.clone(),
+                            sampler_sigmas=sampler.discretization(steps)), os.path.join(GOLDEN_DIR, "sampler_tv2v.pt"))
+            print("sampler done:", len(calls), "network calls", round(time.time() - t0, 1), "s", flush=True)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.manual_seed(0)
+    for kind in (sys.argv[1:] or ["tv2v", "tvi2v"]):
+        run(kind)
