@@ -191,6 +191,21 @@ __global__ void add_center_frame_kernel(__half* __restrict__ x, const __half* __
   *xp = add8(*xp, __ldg(reinterpret_cast<const uint4*>(y) + i));
 }
 
+// fp32 -> fp16 cast of a flat buffer (the text context c["crossattn"], wrappers.py:164-166 casts to the model dtype)
+__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(src + i));
+    __half2 a = __floats2half2_rn(f.x, f.y), b = __floats2half2_rn(f.z, f.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + i) = u;
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2half_rn(src[j]);
+  }
+}
+
 static inline unsigned blocks_for(long long total, int threads) {
   return static_cast<unsigned>((total + threads - 1) / threads);
 }
@@ -307,5 +322,17 @@ extern "C" int ccedit_add_center_frame(void* x, const void* y, int32_t B, int32_
       static_cast<__half*>(x), static_cast<const __half*>(y), T, HWnvec, total);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_add_center_frame");
+  return CCEDIT_OK;
+}
+
+
+extern "C" int ccedit_to_half(const float* src, void* dst, int64_t n, void* stream) {
+  CCEDIT_CHECK_ARG(src && dst && n > 0, "ccedit_to_half: bad arguments");
+  CCEDIT_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+                   "ccedit_to_half: src must be 16-byte and dst 8-byte aligned");
+  to_half_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__half*>(dst), n);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_to_half");
   return CCEDIT_OK;
 }

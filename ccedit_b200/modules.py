@@ -50,28 +50,37 @@ class ParamHolder(nn.Module):
             self.bias = nn.Parameter(b)
         else:
             self.register_parameter("bias", None)
-        self._cache = None
+        self._cache = {}
 
     def forward(self, *a, **k):  # never used for compute
         raise RuntimeError("ccedit_b200 parameter holders are not callable; use the owning block's forward")
 
-    # ---- packed views -------------------------------------------------------------------------------------------
-    def packed(self, device, geglu=False) -> PackedWeight:
-        c = self._cache
-        if c is None or c[0] != (device, "w", geglu):
-            self._cache = c = ((device, "w", geglu), ops.pack_weight(self.weight, self.bias, device, geglu=geglu))
+    # ---- packed views (rebuilt when the parameter is replaced or modified in place, e.g. by a LoRA merge) ----------
+    def _version(self):
+        b = self.bias
+        return (self.weight.data_ptr(), self.weight._version, None if b is None else (b.data_ptr(), b._version))
+
+    def _cached(self, key, make):
+        ver = self._version()
+        c = self._cache.get(key)
+        if c is None or c[0] != ver:
+            self._cache[key] = c = (ver, make())
         return c[1]
+
+    def packed(self, device, geglu=False, scale: float = 1.0) -> PackedWeight:
+        def make():
+            w = self.weight if scale == 1.0 else self.weight.detach().float() * scale
+            b = self.bias if (scale == 1.0 or self.bias is None) else self.bias.detach().float() * scale
+            return ops.pack_weight(w, b, device, geglu=geglu)
+        return self._cached((device, "w", geglu, scale), make)
 
     def affine(self, device):
-        c = self._cache
-        if c is None or c[0] != (device, "affine"):
-            self._cache = c = ((device, "affine"), (
-                self.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
-                self.bias.detach().to(device=device, dtype=torch.float32).contiguous()))
-        return c[1]
+        return self._cached((device, "affine"), lambda: (
+            self.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
+            self.bias.detach().to(device=device, dtype=torch.float32).contiguous()))
 
     def invalidate(self):
-        self._cache = None
+        self._cache = {}
 
 
 def conv2d(cin, cout, k, zero=False):
@@ -135,11 +144,12 @@ class CrossAttention(nn.Module):
         self._pk = {}
 
     def fused(self, device, which):
-        key = (device, which)
-        if key not in self._pk:
-            hs = {"qkv": [self.to_q, self.to_k, self.to_v], "kv": [self.to_k, self.to_v]}[which]
-            self._pk[key] = _fused(device, hs)
-        return self._pk[key]
+        hs = {"qkv": [self.to_q, self.to_k, self.to_v], "kv": [self.to_k, self.to_v]}[which]
+        ver = tuple(h._version() for h in hs)
+        c = self._pk.get((device, which))
+        if c is None or c[0] != ver:
+            self._pk[(device, which)] = c = (ver, _fused(device, hs))
+        return c[1]
 
     def invalidate(self):
         self._pk = {}
@@ -215,6 +225,7 @@ class SpatialTransformer(nn.Module):
         super().__init__()
         inner = n_heads * d_head
         self.heads = n_heads
+        self.channels = in_channels
         self.disable_text_ca = disable_text_ca
         self.norm = norm(in_channels)
         self.proj_in = conv2d(in_channels, inner, 1)
@@ -449,6 +460,18 @@ class Upsample3D(nn.Module):
 
 class TimestepEmbedSequential(nn.ModuleList):
     """openaimodel.py:85-126: children are applied in order; here every child implements run(x, ctx, out)."""
+
+    @property
+    def out_channels(self) -> int:
+        for layer in reversed(list(self)):
+            for name in ("out_channels", "channels"):
+                if hasattr(layer, name):
+                    return getattr(layer, name)
+        raise AttributeError("no layer with a channel count")
+
+    @property
+    def upsamples(self) -> bool:
+        return any(isinstance(layer, Upsample3D) for layer in self)
 
     def run(self, x, ctx: Ctx, out=None):
         n = len(self)

@@ -438,3 +438,31 @@ def add_center_frame(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     _lib.check(_lib.load().ccedit_add_center_frame(x.data_ptr(), y.data_ptr(), B, T, HW, Cc, _stream()),
                "ccedit_add_center_frame")
     return x
+
+
+def to_half(src: torch.Tensor) -> torch.Tensor:
+    """fp32 (or already fp16) tensor -> contiguous fp16 tensor of the same shape."""
+    if not src.is_cuda:
+        raise RuntimeError("ccedit_b200: src must be a CUDA tensor (no CPU fallback)")
+    if src.dtype == torch.float16:
+        return src.contiguous()
+    src = src.to(torch.float32).contiguous()
+    dst = torch.empty(src.shape, dtype=torch.float16, device=src.device)
+    _lib.check(_lib.load().ccedit_to_half(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "ccedit_to_half")
+    return dst
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# launch accounting (bench.py's gpu_launches): kernels launched by the library + kernels replayed from CUDA graphs
+# ---------------------------------------------------------------------------------------------------------------------
+_GRAPH_LAUNCHES = 0
+
+
+def note_graph_replay(n: int) -> None:
+    global _GRAPH_LAUNCHES
+    _GRAPH_LAUNCHES += int(n)
+
+
+def launch_count() -> int:
+    """Kernels of this library executed so far in this process (direct launches + graph-replayed launches)."""
+    return _lib.launch_count() + _GRAPH_LAUNCHES

@@ -152,6 +152,9 @@ int ccedit_add_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void
 /* x[b][T/2][hw][c] += y[b][hw][c]  (img_control on the centre frame, controlmodel.py:529-535). */
 int ccedit_add_center_frame(void* x, const void* y, int32_t B, int32_t T, int32_t HW, int32_t C, void* stream);
 
+/* dst fp16 [n] = (half) src fp32 [n]  (the cast of c["crossattn"] to the model dtype, wrappers.py:164-166). */
+int ccedit_to_half(const float* src, void* dst, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,87 @@
+"""pytest configuration: `gpu` marker (tests that need a B200), shared fixtures and seeded-weight helpers."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (sm_100a); run with -m gpu on the B200 box")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def manifests():
+    from oracle.weights import load_manifest
+    return {k: load_manifest(k) for k in ("tv2v", "tvi2v")}
+
+
+@pytest.fixture(scope="session")
+def state_dicts(manifests):
+    """Seeded fp32 state dicts (reference key layout, prefix `diffusion_model.`), built lazily per kind."""
+    from oracle.weights import seeded_state_dict
+    cache = {}
+
+    def get(kind):
+        if kind not in cache:
+            cache[kind] = seeded_state_dict(manifests[kind], seed=0)
+        return cache[kind]
+    return get
+
+
+@pytest.fixture(scope="session")
+def gpu_wrappers(state_dicts):
+    """The CUDA networks (ccedit_b200 wrapper around ControlledUNetModel3DTV2V) with the seeded weights loaded."""
+    from oracle.ref_import import yaml_params  # plain dicts of the YAML params; does not touch /root/reference
+    from ccedit_b200.controlmodel import ControlledUNetModel3DTV2V
+    from ccedit_b200.wrappers import OpenAIWrapperControlLDM3DTV2V
+    cache = {}
+
+    def get(kind, graph=False):
+        if kind not in cache:
+            net = ControlledUNetModel3DTV2V(**yaml_params(kind))
+            wrap = OpenAIWrapperControlLDM3DTV2V(net, use_cuda_graph=False)
+            wrap.load_state_dict(state_dicts(kind), strict=True)
+            cache[kind] = wrap.cuda().eval()
+        cache[kind].use_cuda_graph = graph
+        return cache[kind]
+    return get
+
+
+def rel_err(got: torch.Tensor, ref: torch.Tensor) -> float:
+    """max |got - ref| / max |ref| (scale-normalised max error)."""
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+
+
+def assert_close(got, ref, rtol, atol, what=""):
+    """|got - ref| <= atol + rtol * |ref| elementwise (torch.allclose semantics), with a useful message."""
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = err > bound
+    if bool(bad.any()):
+        i = int(torch.argmax(err - bound))
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} elements outside rtol={rtol} atol={atol}; worst "
+                             f"|err|={float(err.flatten()[i]):.3e} at ref={float(ref.flatten()[i]):.3e}; "
+                             f"max|ref|={float(ref.abs().max()):.3e}")
