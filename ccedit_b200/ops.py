@@ -30,6 +30,39 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+# per-launch profiler (bench.py --breakdown / roofline): when enabled every C-ABI call is bracketed by CUDA events on
+# the launching stream and recorded with its algorithmic FLOPs and bytes
+_PROF = None
+
+
+def profile_start() -> None:
+    global _PROF
+    _PROF = []
+
+
+def profile_stop():
+    """-> list of (kernel class, flops, bytes, milliseconds); synchronises the device."""
+    global _PROF
+    recs, _PROF = _PROF or [], None
+    torch.cuda.synchronize()
+    return [(name, fl, by, e0.elapsed_time(e1)) for name, fl, by, e0, e1 in recs]
+
+
+def _call(name: str, fn, args, flops: float = 0.0, nbytes: float = 0.0) -> None:
+    if _PROF is None:
+        _lib.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(fn(*args), name)
+    e1.record()
+    _PROF.append((name, flops, nbytes, e0, e1))
+
+
+def _nb(*ts) -> int:
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
 def _require(t: torch.Tensor, dtype=torch.float16, name="tensor"):
     if not t.is_cuda:
         raise RuntimeError(f"ccedit_b200: {name} must be a CUDA tensor (no CPU fallback)")
@@ -222,7 +255,12 @@ def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = 
         for i in range(4):
             arr[i] = rstr[i]
     d.flags = (_lib.GEMM_SILU if silu else 0) | (_lib.GEMM_GEGLU if pw.geglu else 0)
-    _lib.check(_lib.load().ccedit_gemm(C.byref(d), _stream()), "ccedit_gemm")
+    m_rows = math.prod(odims)
+    kind = {1: "gemm.linear", 3: "gemm.temporal_k3", 9: "gemm.conv3x3"}.get(len(taps), "gemm.other")
+    if pw.geglu:
+        kind = "gemm.linear_geglu"
+    _call(kind, _lib.load().ccedit_gemm, (C.byref(d), _stream()), flops=2.0 * m_rows * pw.ntaps * min(c, pw.k) * pw.n,
+          nbytes=_nb(a, pw.w, out, res1, res2))
     return out
 
 
@@ -251,9 +289,9 @@ def groupnorm_spatial(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, 
     F, Cc = x.shape[0], x.shape[-1]
     HW = x.numel() // (F * Cc)
     out = torch.empty_like(x) if out is None else out
-    _lib.check(_lib.load().ccedit_groupnorm_spatial(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                                   _gn_scratch(x.device, F).data_ptr(), F, HW, Cc, eps, int(silu),
-                                                   _stream()), "ccedit_groupnorm_spatial")
+    _call("groupnorm_spatial", _lib.load().ccedit_groupnorm_spatial,
+          (x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _gn_scratch(x.device, F).data_ptr(), F, HW, Cc,
+           eps, int(silu), _stream()), nbytes=_nb(x, out))
     return out
 
 
@@ -266,9 +304,9 @@ def groupnorm_temporal(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
     B, T, Cc = x.shape[0], x.shape[1], x.shape[-1]
     HW = x.numel() // (B * T * Cc)
     out = torch.empty_like(x) if out is None else out
-    _lib.check(_lib.load().ccedit_groupnorm_temporal(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                                    B, T, HW, Cc, eps, int(silu), _stream()),
-               "ccedit_groupnorm_temporal")
+    _call("groupnorm_temporal", _lib.load().ccedit_groupnorm_temporal,
+          (x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, T, HW, Cc, eps, int(silu), _stream()),
+          nbytes=_nb(x, out))
     return out
 
 
@@ -288,8 +326,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         raise RuntimeError("ccedit_b200.layernorm: channel dimension must be contiguous")
     ldx = x2.stride(0)
     out = torch.empty(x.shape, dtype=torch.float16, device=x.device) if out is None else out
-    _lib.check(_lib.load().ccedit_layernorm(x2.data_ptr(), ldx, out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M,
-                                           Cc, eps, _stream()), "ccedit_layernorm")
+    _call("layernorm", _lib.load().ccedit_layernorm,
+          (x2.data_ptr(), ldx, out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M, Cc, eps, _stream()), nbytes=2 * _nb(out))
     return out
 
 
@@ -330,7 +368,10 @@ def attention(q: torch.Tensor, segments: Sequence[KVSegment], heads: int, out: t
         a.kv_div[s], a.kv_mul[s], a.kv_add[s] = seg.div, seg.mul, seg.add
     a.frames, a.lq, a.heads, a.d = F, L, heads, dh
     a.scale = float(dh) ** -0.5 if scale is None else scale
-    _lib.check(_lib.load().ccedit_attention(C.byref(a), _stream()), "ccedit_attention")
+    lkv = sum(seg.k.shape[1] for seg in segments)
+    kvb = sum(2.0 * seg.k.shape[0] * seg.k.shape[1] * Cc * 2 for seg in segments)   # each K/V row read once (ideal)
+    _call("attention", _lib.load().ccedit_attention, (C.byref(a), _stream()), flops=4.0 * F * L * lkv * Cc,
+          nbytes=2.0 * F * L * Cc * 2 + kvb)
     return out
 
 
@@ -342,9 +383,9 @@ def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads:
     B, T, HW, Cc = q.shape
     dh = Cc // heads
     sc = float(dh) ** -0.5 if scale is None else scale
-    _lib.check(_lib.load().ccedit_temporal_attention(q.data_ptr(), q.stride(2), k.data_ptr(), k.stride(2), v.data_ptr(),
-                                                    v.stride(2), out.data_ptr(), out.stride(2), B, T, HW, heads, dh,
-                                                    sc, _stream()), "ccedit_temporal_attention")
+    _call("temporal_attention", _lib.load().ccedit_temporal_attention,
+          (q.data_ptr(), q.stride(2), k.data_ptr(), k.stride(2), v.data_ptr(), v.stride(2), out.data_ptr(), out.stride(2),
+           B, T, HW, heads, dh, sc, _stream()), flops=4.0 * B * HW * T * T * Cc, nbytes=4.0 * B * T * HW * Cc * 2)
     return out
 
 
@@ -360,8 +401,9 @@ def ncthw_to_cl(src: torch.Tensor, cpad: int, mul: float = 1.0, add: float = 0.0
     src = src.contiguous()
     B, Cin, T, H, W = src.shape
     dst = torch.empty(B, T, H, W, cpad, dtype=torch.float16, device=src.device)
-    _lib.check(_lib.load().ccedit_ncthw_to_cl(src.data_ptr(), int(src.dtype == torch.float32), dst.data_ptr(), B, Cin,
-                                             T, H, W, cpad, mul, add, _stream()), "ccedit_ncthw_to_cl")
+    _call("ncthw_to_cl", _lib.load().ccedit_ncthw_to_cl,
+          (src.data_ptr(), int(src.dtype == torch.float32), dst.data_ptr(), B, Cin, T, H, W, cpad, mul, add, _stream()),
+          nbytes=_nb(src, dst))
     return dst
 
 
@@ -370,17 +412,17 @@ def out_temporal(y: torch.Tensor, wt: torch.Tensor, bias_t: torch.Tensor, cout: 
     _require(y, name="y")
     B, T, H, W, ld = y.shape
     dst = torch.empty(B, cout, T, H, W, dtype=out_dtype, device=y.device)
-    _lib.check(_lib.load().ccedit_out_temporal(y.data_ptr(), ld, wt.data_ptr(), bias_t.data_ptr(), dst.data_ptr(),
-                                              int(out_dtype == torch.float32), B, cout, T, H * W, _stream()),
-               "ccedit_out_temporal")
+    _call("out_temporal", _lib.load().ccedit_out_temporal,
+          (y.data_ptr(), ld, wt.data_ptr(), bias_t.data_ptr(), dst.data_ptr(), int(out_dtype == torch.float32), B, cout, T,
+           H * W, _stream()), nbytes=_nb(y, dst))
     return dst
 
 
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     tf = t.to(torch.float32).contiguous()
     out = torch.empty(tf.shape[0], dim, dtype=torch.float32, device=tf.device)
-    _lib.check(_lib.load().ccedit_timestep_embedding(tf.data_ptr(), out.data_ptr(), tf.shape[0], dim, max_period,
-                                                    _stream()), "ccedit_timestep_embedding")
+    _call("timestep_embedding", _lib.load().ccedit_timestep_embedding,
+          (tf.data_ptr(), out.data_ptr(), tf.shape[0], dim, max_period, _stream()), nbytes=_nb(out))
     return out
 
 
@@ -392,8 +434,9 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], ac
     M, K = x.shape
     N = w.shape[0]
     out = torch.empty(M, N, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().ccedit_linear_small(x.data_ptr(), w.data_ptr(), _ptr(b), out.data_ptr(), M, N, K,
-                                              int(act_in), int(act_out), _stream()), "ccedit_linear_small")
+    _call("linear_small", _lib.load().ccedit_linear_small,
+          (x.data_ptr(), w.data_ptr(), _ptr(b), out.data_ptr(), M, N, K, int(act_in), int(act_out), _stream()),
+          flops=2.0 * M * N * K, nbytes=_nb(x, w, out))
     return out
 
 
@@ -402,8 +445,8 @@ def parity_split(x: torch.Tensor) -> torch.Tensor:
     _require(x, name="x")
     F, H, W, Cc = x.shape
     y = torch.empty(F, 4, H // 2, W // 2, Cc, dtype=torch.float16, device=x.device)
-    _lib.check(_lib.load().ccedit_parity_split(x.data_ptr(), y.data_ptr(), F, H, W, Cc, _stream()),
-               "ccedit_parity_split")
+    _call("parity_split", _lib.load().ccedit_parity_split, (x.data_ptr(), y.data_ptr(), F, H, W, Cc, _stream()),
+          nbytes=_nb(x, y))
     return y
 
 
@@ -412,8 +455,8 @@ def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
     _require(x, name="x")
     F, H, W, Cc = x.shape
     y = torch.empty(F, 2 * H, 2 * W, Cc, dtype=torch.float16, device=x.device)
-    _lib.check(_lib.load().ccedit_upsample_nearest2x(x.data_ptr(), y.data_ptr(), F, H, W, Cc, _stream()),
-               "ccedit_upsample_nearest2x")
+    _call("upsample_nearest2x", _lib.load().ccedit_upsample_nearest2x, (x.data_ptr(), y.data_ptr(), F, H, W, Cc, _stream()),
+          nbytes=_nb(x, y))
     return y
 
 
@@ -423,8 +466,9 @@ def add_rows(a: torch.Tensor, b: Optional[torch.Tensor], dst: torch.Tensor) -> t
     M = a.numel() // Cc
     a2, d2 = a.reshape(M, Cc) if a.is_contiguous() else a.view(M, Cc), dst.view(M, Cc)
     b2 = None if b is None else (b.reshape(M, Cc) if b.is_contiguous() else b.view(M, Cc))
-    _lib.check(_lib.load().ccedit_add_rows(a2.data_ptr(), a2.stride(0), _ptr(b2), 0 if b2 is None else b2.stride(0),
-                                          d2.data_ptr(), d2.stride(0), M, Cc, _stream()), "ccedit_add_rows")
+    _call("add_rows", _lib.load().ccedit_add_rows,
+          (a2.data_ptr(), a2.stride(0), _ptr(b2), 0 if b2 is None else b2.stride(0), d2.data_ptr(), d2.stride(0), M, Cc,
+           _stream()), nbytes=_nb(a, b) + M * Cc * 2)
     return dst
 
 
@@ -435,8 +479,8 @@ def add_center_frame(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     B, T = x.shape[0], x.shape[1]
     Cc = x.shape[-1]
     HW = x.numel() // (B * T * Cc)
-    _lib.check(_lib.load().ccedit_add_center_frame(x.data_ptr(), y.data_ptr(), B, T, HW, Cc, _stream()),
-               "ccedit_add_center_frame")
+    _call("add_center_frame", _lib.load().ccedit_add_center_frame, (x.data_ptr(), y.data_ptr(), B, T, HW, Cc, _stream()),
+          nbytes=3 * _nb(y))
     return x
 
 
@@ -448,7 +492,8 @@ def to_half(src: torch.Tensor) -> torch.Tensor:
         return src.contiguous()
     src = src.to(torch.float32).contiguous()
     dst = torch.empty(src.shape, dtype=torch.float16, device=src.device)
-    _lib.check(_lib.load().ccedit_to_half(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "ccedit_to_half")
+    _call("to_half", _lib.load().ccedit_to_half, (src.data_ptr(), dst.data_ptr(), src.numel(), _stream()),
+          nbytes=_nb(src, dst))
     return dst
 
 

@@ -1,0 +1,223 @@
+"""GPU parity of every C-ABI kernel against the oracle's leaf ops (oracle/sgm_oracle.py: F.conv2d / F.linear /
+F.group_norm / F.layer_norm / SDPA in fp32) on identical fp16-rounded operands.
+
+Tolerance (north_star): rtol = 1e-3, atol = 1e-4 - scaled by max|ref| for the absolute part, because the outputs are
+stored in fp16 (relative rounding 4.9e-4) and the operands are not normalised to unit scale."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def close(got, ref, what, rtol=RTOL, atol=ATOL):
+    assert_close(got, ref, rtol, atol * max(1.0, float(ref.abs().max())), what)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from ccedit_b200 import ops
+    return ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).half()
+
+
+@pytest.mark.parametrize("M,K,N,geglu,res", [(128, 64, 16, False, False), (256, 320, 320, False, False),
+                                              (1000, 320, 960, False, False), (3264, 1280, 1280, False, True),
+                                              (500, 320, 2560, True, False), (154, 768, 640, False, False),
+                                              (1, 320, 320, False, False), (4096, 1280, 320, False, True)])
+def test_linear(ops, M, K, N, geglu, res):
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K))
+    b = rnd(N, seed=3).float()
+    r = rnd(M, N // 2 if geglu else N, seed=4) if res else None
+    pw = ops.pack_weight(w.float(), b, "cuda", geglu=geglu)
+    out = torch.empty(M, pw.n_out, dtype=torch.float16, device="cuda")
+    ops.gemm(a.cuda(), pw, out, res1=None if r is None else r.cuda())
+    ref = F.linear(a.float(), w.float(), b)
+    if geglu:
+        v, g = ref.chunk(2, dim=-1)
+        ref = v * F.gelu(g)
+    if res:
+        ref = ref + r.float()
+    close(out, ref, f"linear {M}x{K}x{N}")
+
+
+@pytest.mark.parametrize("Fr,H,W,Cin,Cout,emb,silu", [(2, 16, 24, 64, 64, False, False), (4, 8, 12, 320, 320, True, False),
+                                                      (2, 32, 48, 8, 320, False, False), (2, 64, 96, 320, 4, False, False),
+                                                      (2, 32, 32, 16, 32, False, True), (3, 16, 24, 960, 640, False, False),
+                                                      (1, 5, 7, 64, 64, False, False)])
+def test_conv3x3(ops, Fr, H, W, Cin, Cout, emb, silu):
+    x, w = rnd(Fr, Cin, H, W, seed=5), rnd(Cout, Cin, 3, 3, seed=6, scale=1 / math.sqrt(9 * Cin))
+    b = rnd(Cout, seed=7).float()
+    T = 2 if Fr % 2 == 0 else 1
+    pw = ops.pack_weight(w.float(), b, "cuda")
+    rb = rnd(Fr // T, pw.n, seed=8).float() if emb else None
+    out = torch.empty(Fr, H, W, pw.n, dtype=torch.float16, device="cuda")
+    ops.gemm(x.permute(0, 2, 3, 1).contiguous().cuda(), pw, out, ops.conv_taps(),
+             rowbias=None if rb is None else rb.cuda(), rb_dim=2, rb_div=T, silu=silu)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1)
+    if emb:
+        ref = ref + rb[:, :Cout].repeat_interleave(T, 0)[:, :, None, None]
+    if silu:
+        ref = F.silu(ref)
+    close(out[..., :Cout].permute(0, 3, 1, 2), ref, f"conv3x3 {Cin}->{Cout}")
+
+
+@pytest.mark.parametrize("Fr,H,W,C", [(2, 16, 24, 64), (3, 64, 96, 320), (2, 8, 12, 1280), (2, 32, 48, 16)])
+def test_conv3x3_stride2(ops, Fr, H, W, C):
+    x, w = rnd(Fr, C, H, W, seed=9), rnd(C, C, 3, 3, seed=10, scale=1 / math.sqrt(9 * C))
+    b = rnd(C, seed=11).float()
+    pw = ops.pack_weight(w.float(), b, "cuda")
+    planes = ops.parity_split(x.permute(0, 2, 3, 1).contiguous().cuda())
+    out = torch.empty(Fr, 1, H // 2, W // 2, C, dtype=torch.float16, device="cuda")
+    ops.gemm(planes, pw, out, ops.conv_s2_taps())
+    ref = F.conv2d(x.float(), w.float(), b, stride=2, padding=1)
+    close(out[:, 0].permute(0, 3, 1, 2), ref, f"conv3x3/s2 C={C}")
+
+
+@pytest.mark.parametrize("B,T,HW,C", [(2, 17, 50, 320), (1, 3, 24, 1280), (2, 1, 16, 64), (1, 33, 20, 640)])
+def test_temporal_conv_k3_with_identity(ops, B, T, HW, C):
+    """spatial_temporal_forward's temporal half: y + conv1d_k3(y) over T per pixel, zero padded at the clip ends."""
+    y, w = rnd(B, T, HW, C, seed=12), rnd(C, C, 3, seed=13, scale=1 / math.sqrt(3 * C))
+    b = rnd(C, seed=14).float()
+    pw = ops.pack_weight(w.float(), b, "cuda")
+    yc = y.cuda()
+    out = ops.gemm(yc, pw, torch.empty_like(yc), ops.temporal_taps(3), res1=yc)
+    z = y.float().permute(0, 2, 3, 1).reshape(B * HW, C, T)                      # (b hw) c t
+    ref = (z + F.conv1d(z, w.float(), b, padding=1)).reshape(B, HW, C, T).permute(0, 3, 1, 2)
+    close(out, ref, f"temporal conv T={T} C={C}")
+
+
+@pytest.mark.parametrize("Fr,HW,C,eps,silu", [(2, 96, 320, 1e-5, True), (3, 6144, 320, 1e-6, False),
+                                              (2, 24, 2560, 1e-5, True), (1, 1, 64, 1e-5, False), (2, 1536, 960, 1e-5, True)])
+def test_groupnorm_spatial(ops, Fr, HW, C, eps, silu):
+    x = rnd(Fr, HW, C, seed=15) + 0.5
+    g, b = rnd(C, seed=16).float() * 0.1 + 1, rnd(C, seed=17).float() * 0.1
+    out = ops.groupnorm_spatial(x.cuda(), g.cuda(), b.cuda(), eps, silu)
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, g, b, eps)
+    if silu:
+        ref = F.silu(ref)
+    close(out, ref.permute(0, 2, 1), f"GN spatial C={C}")
+
+
+@pytest.mark.parametrize("B,T,HW,C,silu", [(2, 17, 40, 320, True), (1, 3, 24, 1280, False), (2, 33, 10, 640, True),
+                                           (1, 1, 7, 64, False)])
+def test_groupnorm_temporal(ops, B, T, HW, C, silu):
+    x = rnd(B, T, HW, C, seed=18) + 0.25
+    g, b = rnd(C, seed=19).float() * 0.1 + 1, rnd(C, seed=20).float() * 0.1
+    out = ops.groupnorm_temporal(x.cuda(), g.cuda(), b.cuda(), 1e-5, silu)
+    z = x.float().permute(0, 2, 3, 1).reshape(B * HW, C, T)
+    ref = F.group_norm(z, 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    close(out, ref.reshape(B, HW, C, T).permute(0, 3, 1, 2), f"GN temporal C={C} T={T}")
+
+
+@pytest.mark.parametrize("M,C", [(513, 1280), (64, 64), (1000, 320), (7, 640)])
+def test_layernorm(ops, M, C):
+    x = rnd(M, C, seed=21) * 2 + 0.3
+    g, b = rnd(C, seed=22).float() * 0.1 + 1, rnd(C, seed=23).float() * 0.1
+    out = ops.layernorm(x.cuda(), g.cuda(), b.cuda())
+    close(out, F.layer_norm(x.float(), (C,), g, b, 1e-5), f"LN C={C}")
+
+
+def _sdpa(q, k, v, heads):
+    Fq, L, C = q.shape
+    sp = lambda t: t.float().view(t.shape[0], t.shape[1], heads, C // heads).transpose(1, 2)
+    o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v))
+    return o.transpose(1, 2).reshape(Fq, L, C)
+
+
+@pytest.mark.parametrize("Fr,L,Lkv,heads,d", [(3, 384, 384, 8, 40), (2, 200, 200, 8, 80), (2, 96, 96, 8, 160),
+                                              (4, 300, 77, 8, 40), (2, 128, 128, 4, 16), (2, 1536, 1536, 8, 80),
+                                              (1, 1, 1, 8, 40), (1, 6144, 6144, 8, 40)])
+def test_attention(ops, Fr, L, Lkv, heads, d):
+    C = heads * d
+    q, k, v = rnd(Fr, L, C, seed=24), rnd(Fr, Lkv, C, seed=25), rnd(Fr, Lkv, C, seed=26)
+    out = torch.empty(Fr, L, C, dtype=torch.float16, device="cuda")
+    ops.attention(q.cuda(), [ops.KVSegment(k.cuda(), v.cuda())], heads, out)
+    close(out, _sdpa(q, k, v, heads), f"attention L={L} Lkv={Lkv} d={d}")
+
+
+def test_attention_text_keys_shared_by_frames(ops):
+    """Text cross-attention: all T frames of a batch entry read the same 77 keys (attention.py:1159-1163)."""
+    B, T, L, heads, d = 2, 3, 100, 8, 40
+    C = heads * d
+    q, k, v = rnd(B * T, L, C, seed=27), rnd(B, 77, C, seed=28), rnd(B, 77, C, seed=29)
+    out = torch.empty(B * T, L, C, dtype=torch.float16, device="cuda")
+    ops.attention(q.cuda(), [ops.KVSegment(k.cuda(), v.cuda(), div=T)], heads, out)
+    ref = _sdpa(q, k.repeat_interleave(T, 0), v.repeat_interleave(T, 0), heads)
+    close(out, ref, "text attention")
+
+
+def test_attention_center_self_two_segments(ops):
+    """cfca: K/V = cat([centre-frame tokens (repeated over t), own tokens]) (attention.py:1323-1336)."""
+    B, T, L, heads, d = 2, 3, 70, 8, 40
+    C = heads * d
+    q, k, v = rnd(B * T, L, C, seed=30), rnd(B * T, L, C, seed=31), rnd(B * T, L, C, seed=32)
+    out = torch.empty(B * T, L, C, dtype=torch.float16, device="cuda")
+    kc, vc = k.cuda(), v.cuda()
+    ops.attention(q.cuda(), [ops.KVSegment(kc, vc, div=T, mul=T, add=T // 2), ops.KVSegment(kc, vc)], heads, out)
+    ctr = lambda t: t.view(B, T, L, C)[:, T // 2].repeat_interleave(T, 0)
+    ref = _sdpa(q, torch.cat([ctr(k), k], 1), torch.cat([ctr(v), v], 1), heads)
+    close(out, ref, "center_self attention")
+
+
+@pytest.mark.parametrize("B,T,HW,heads,d", [(2, 17, 50, 8, 40), (1, 9, 30, 8, 160), (2, 33, 20, 8, 80), (1, 1, 5, 8, 40)])
+def test_temporal_attention(ops, B, T, HW, heads, d):
+    C = heads * d
+    q, k, v = rnd(B, T, HW, C, seed=33), rnd(B, T, HW, C, seed=34), rnd(B, T, HW, C, seed=35)
+    out = torch.empty(B, T, HW, C, dtype=torch.float16, device="cuda")
+    ops.temporal_attention(q.cuda(), k.cuda(), v.cuda(), heads, out)
+    tok = lambda t: t.permute(0, 2, 1, 3).reshape(B * HW, T, C)                   # (b hw) t c
+    ref = _sdpa(tok(q), tok(k), tok(v), heads).view(B, HW, T, C).permute(0, 2, 1, 3)
+    close(out, ref, f"temporal attention T={T} d={d}")
+
+
+def test_layout_and_small_kernels(ops):
+    x = torch.randn(2, 3, 4, 16, 24, generator=torch.Generator().manual_seed(36))
+    cl = ops.ncthw_to_cl(x.cuda(), 8, mul=-0.5, add=0.5)
+    ref = torch.zeros(2, 4, 16, 24, 8)
+    ref[..., :3] = (0.5 - 0.5 * x).permute(0, 2, 3, 4, 1)
+    close(cl, ref, "ncthw_to_cl (hint transform)")
+    t = torch.tensor([0.0, 417.0, 999.0])
+    from oracle.sgm_oracle import timestep_embedding
+    assert_close(ops.timestep_embedding(t.cuda(), 320), timestep_embedding(t, 320), 1e-4, 2e-4, "timestep embedding")
+    xs, w, b = torch.randn(3, 320), rnd(1280, 320, seed=37, scale=0.05), torch.randn(1280) * 0.1
+    got = ops.linear_small(xs.cuda(), w.cuda(), b.cuda(), act_in=True, act_out=True)
+    assert_close(got, F.silu(F.linear(F.silu(xs), w.float(), b)), 1e-4, 1e-5, "linear_small")
+    u = rnd(2, 6, 8, 64, seed=38)
+    assert torch.equal(ops.upsample_nearest2x(u.cuda()).cpu(),
+                       F.interpolate(u.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).half())
+    a, bb = rnd(2, 3, 10, 64, seed=39), rnd(2, 3, 10, 64, seed=40)
+    dst = torch.zeros(2, 3, 10, 128, dtype=torch.float16, device="cuda")
+    ops.add_rows(a.cuda(), bb.cuda(), dst[..., 64:])
+    close(dst[..., 64:], a.float() + bb.float(), "add_rows")
+    assert float(dst[..., :64].abs().max()) == 0.0
+    x5, y4 = rnd(2, 5, 12, 64, seed=41), rnd(2, 12, 64, seed=42)
+    x5c = x5.cuda()
+    ops.add_center_frame(x5c, y4.cuda())
+    ref = x5.float().clone()
+    ref[:, 2] += y4.float()
+    close(x5c, ref, "add_center_frame")
+    c32 = torch.randn(2, 77, 768)
+    assert torch.equal(ops.to_half(c32.cuda()).cpu(), c32.half())
+
+
+def test_errors_are_loud(ops):
+    """Bad arguments raise with the library's message instead of computing something else."""
+    a = torch.zeros(128, 64, dtype=torch.float16, device="cuda")
+    pw = ops.pack_weight(torch.zeros(16, 64), None, "cuda")
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.gemm(a.cpu(), pw, torch.empty(128, 16, dtype=torch.float16))
+    with pytest.raises(RuntimeError):
+        ops.groupnorm_spatial(torch.zeros(1, 4, 48, dtype=torch.float16, device="cuda"), torch.ones(48).cuda(),
+                              torch.zeros(48).cuda(), 1e-5, False)     # 48 channels: not a multiple of 32
