@@ -246,80 +246,111 @@ static int launch_fa(const FaParams& p, int frames, int heads, cudaStream_t st) 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// temporal attention: grid (B*HW, heads/wpb); one warp per head.
+// temporal attention: one CTA per pixel, one warp per head, one lane per query frame.
+//   phase 1: the CTA streams the pixel's q, k, v rows ([T][C], C = heads*d contiguous) into shared memory with
+//            16-byte cp.async (fully coalesced rows, everything in flight at once: this kernel is HBM-bound);
+//   phase 2: lane i of warp h holds query frame i of head h: scores against all T keys (K rows are read as
+//            warp-wide broadcasts), softmax in registers / a per-warp scratch column, P.V in 8-channel chunks.
+// Row stride in smem is C+8 halves so that the per-lane q reads (different rows) are bank-conflict free.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
 __global__ void temporal_attn_kernel(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k,
                                      long long ldk, const __half* __restrict__ v, long long ldv, __half* __restrict__ o,
-                                     long long ldo, int T, int HW, int d, float scale_log2) {
+                                     long long ldo, int T, int HW, int heads, int d, float scale_log2) {
+  // `heads` = heads handled by this CTA (a head group when T*C does not fit in shared memory); blockIdx.y = group
   extern __shared__ __align__(16) uint8_t ta_smem[];
+  const int C = heads * d;
+  const long long col0 = static_cast<long long>(blockIdx.y) * C;
+  q += col0;
+  k += col0;
+  v += col0;
+  o += col0;
+  const int RS = C + 8;                                   // smem row stride (halves)
+  __half* sq = reinterpret_cast<__half*>(ta_smem);        // [T][RS]
+  __half* sk = sq + static_cast<size_t>(T) * RS;
+  __half* sv = sk + static_cast<size_t>(T) * RS;
+  float* sp = reinterpret_cast<float*>(sv + static_cast<size_t>(T) * RS);  // [heads][T][32] scores / probabilities
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const int head = blockIdx.y * wpb + warp;
-  const long long pix = blockIdx.x;  // b*HW + hw
+  const long long pix = blockIdx.x;                       // b*HW + hw
   const int b = static_cast<int>(pix / HW), hw = static_cast<int>(pix % HW);
-  const int dw = d >> 1;        // 32-bit words per row
-  const int rs = dw + 1;        // padded row stride (odd) in words
-  uint32_t* sq = reinterpret_cast<uint32_t*>(ta_smem) + static_cast<size_t>(warp) * 3 * T * rs;
-  uint32_t* sk = sq + T * rs;
-  uint32_t* sv = sk + T * rs;
-  const long long row0 = (static_cast<long long>(b) * T) * HW + hw;  // row index of frame 0; frame t adds t*HW
-  for (int i = lane; i < T * dw; i += 32) {
-    const int t = i / dw, w = i % dw;
+  const long long row0 = (static_cast<long long>(b) * T) * HW + hw;  // row of frame 0; frame t adds t*HW
+  const int cpr = C >> 3;                                 // 16-byte chunks per row
+  for (int i = threadIdx.x; i < T * cpr; i += blockDim.x) {
+    const int t = i / cpr, c = i - t * cpr;
     const long long row = row0 + static_cast<long long>(t) * HW;
-    sq[t * rs + w] = __ldg(reinterpret_cast<const uint32_t*>(q + row * ldq + head * d) + w);
-    sk[t * rs + w] = __ldg(reinterpret_cast<const uint32_t*>(k + row * ldk + head * d) + w);
-    sv[t * rs + w] = __ldg(reinterpret_cast<const uint32_t*>(v + row * ldv + head * d) + w);
+    cp_async_16(smem_u32(sq + t * RS + c * 8), q + row * ldq + c * 8, true);
+    cp_async_16(smem_u32(sk + t * RS + c * 8), k + row * ldk + c * 8, true);
+    cp_async_16(smem_u32(sv + t * RS + c * 8), v + row * ldv + c * 8, true);
   }
-  __syncwarp();
-  const int j0 = lane, j1 = lane + 32;  // key slots of this lane (T <= 64)
-  for (int i = 0; i < T; ++i) {
-    float s0 = 0.f, s1 = 0.f;
-    const uint32_t* qi = sq + i * rs;
-    if (j0 < T) {
-      const uint32_t* kj = sk + j0 * rs;
-      for (int w = 0; w < dw; ++w) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&qi[w]));
-        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&kj[w]));
-        s0 = fmaf(a.x, c.x, s0);
-        s0 = fmaf(a.y, c.y, s0);
-      }
-    }
-    if (j1 < T) {
-      const uint32_t* kj = sk + j1 * rs;
-      for (int w = 0; w < dw; ++w) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&qi[w]));
-        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&kj[w]));
-        s1 = fmaf(a.x, c.x, s1);
-        s1 = fmaf(a.y, c.y, s1);
-      }
-    }
-    s0 = j0 < T ? s0 * scale_log2 : -INFINITY;
-    s1 = j1 < T ? s1 * scale_log2 : -INFINITY;
-    float m = fmaxf(s0, s1);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    const float p0 = exp2f(s0 - m), p1 = exp2f(s1 - m);
-    float l = p0 + p1;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-    const float inv = 1.f / l;
-    const long long orow = row0 + static_cast<long long>(i) * HW;
-    uint32_t* op = reinterpret_cast<uint32_t*>(o + orow * ldo + head * d);
-    for (int w0 = 0; w0 < dw; w0 += 32) {
-      const int w = w0 + lane;
-      float ax = 0.f, ay = 0.f;
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int nchunk = d >> 3;
+  for (int head = warp; head < heads; head += (blockDim.x >> 5)) {
+    float* spw = sp + static_cast<size_t>(head) * T * 32;
+    for (int i0 = 0; i0 < T; i0 += 32) {
+      const int i = i0 + lane;
+      const bool act = i < T;
+      const __half* qi = sq + (act ? i : 0) * RS + head * d;
+      // ---- scores ----
+      float m = -INFINITY;
       for (int j = 0; j < T; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
-        if (w < dw) {
-          const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(&sv[j * rs + w]));
-          ax = fmaf(pj, vv.x, ax);
-          ay = fmaf(pj, vv.y, ay);
+        const __half* kj = sk + j * RS + head * d;
+        float s = 0.f;
+        for (int c = 0; c < nchunk; ++c) {
+          float a[8], bb[8];
+          unpack8h(*reinterpret_cast<const uint4*>(qi + c * 8), a);
+          unpack8h(*reinterpret_cast<const uint4*>(kj + c * 8), bb);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s = fmaf(a[e], bb[e], s);
+        }
+        s *= scale_log2;
+        spw[j * 32 + lane] = s;
+        m = fmaxf(m, s);
+      }
+      float l = 0.f;
+      for (int j = 0; j < T; ++j) {
+        const float p = exp2f(spw[j * 32 + lane] - m);
+        spw[j * 32 + lane] = p;
+        l += p;
+      }
+      const float inv = 1.f / l;
+      // ---- O = P V, 8 channels at a time ----
+      __half* op = o + (row0 + static_cast<long long>(act ? i : 0) * HW) * ldo + head * d;
+      for (int c = 0; c < nchunk; ++c) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int j = 0; j < T; ++j) {
+          const float p = spw[j * 32 + lane];
+          float vv[8];
+          unpack8h(*reinterpret_cast<const uint4*>(sv + j * RS + head * d + c * 8), vv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vv[e], acc[e]);
+        }
+        if (act) {
+          uint4 u;
+          __half2 h0 = __floats2half2_rn(acc[0] * inv, acc[1] * inv), h1 = __floats2half2_rn(acc[2] * inv, acc[3] * inv);
+          __half2 h2 = __floats2half2_rn(acc[4] * inv, acc[5] * inv), h3 = __floats2half2_rn(acc[6] * inv, acc[7] * inv);
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(op + c * 8) = u;
         }
       }
-      if (w < dw) {
-        __half2 r = __floats2half2_rn(ax * inv, ay * inv);
-        op[w] = *reinterpret_cast<uint32_t*>(&r);
-      }
+      __syncwarp();
     }
   }
 }
@@ -375,16 +406,20 @@ extern "C" int ccedit_temporal_attention(const void* q, int64_t ldq, const void*
                                          int64_t ldv, void* o, int64_t ldo, int32_t B, int32_t T, int32_t HW,
                                          int32_t heads, int32_t d, float scale, void* stream) {
   CCEDIT_CHECK_ARG(q && k && v && o, "ccedit_temporal_attention: null pointer");
-  CCEDIT_CHECK_ARG(B > 0 && T > 0 && T <= 64 && HW > 0 && heads > 0 && d > 0 && d % 2 == 0,
-                   "ccedit_temporal_attention: bad shape B=%d T=%d HW=%d heads=%d d=%d (T<=64)", B, T, HW, heads, d);
-  CCEDIT_CHECK_ARG(ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0, "ccedit_temporal_attention: odd stride");
-  const size_t per_warp = static_cast<size_t>(3) * T * (d / 2 + 1) * 4;
-  int wpb = 8;
-  while (wpb > 1 && (heads % wpb != 0 || per_warp * wpb > 200 * 1024)) wpb >>= 1;
-  CCEDIT_CHECK_ARG(per_warp * wpb <= 227 * 1024, "ccedit_temporal_attention: T*d too large for shared memory");
-  const size_t smem = per_warp * wpb;
+  CCEDIT_CHECK_ARG(B > 0 && T > 0 && T <= 64 && HW > 0 && heads > 0 && d > 0 && d % 8 == 0,
+                   "ccedit_temporal_attention: bad shape B=%d T=%d HW=%d heads=%d d=%d (T<=64, d%%8==0)", B, T, HW, heads, d);
+  CCEDIT_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+                   "ccedit_temporal_attention: row strides must be multiples of 8 elements");
+  CCEDIT_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                     reinterpret_cast<uintptr_t>(o)) & 15) == 0,
+                   "ccedit_temporal_attention: q/k/v/o must be 16-byte aligned");
+  int hpb = heads;   // heads per CTA: all of them unless the pixel's q/k/v rows do not fit in shared memory
+  auto smem_for = [&](int h) { return static_cast<size_t>(3) * T * (h * d + 8) * 2 + static_cast<size_t>(h) * T * 32 * 4; };
+  while (hpb > 1 && (smem_for(hpb) > 200 * 1024 || heads % hpb != 0)) --hpb;
+  const size_t smem = smem_for(hpb);
+  CCEDIT_CHECK_ARG(smem <= 227 * 1024, "ccedit_temporal_attention: T*d too large for shared memory (%zu bytes)", smem);
   static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  if (smem > 48 * 1024 && smem_set == 0) {
     cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_last_error("ccedit_temporal_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -392,10 +427,11 @@ extern "C" int ccedit_temporal_attention(const void* q, int64_t ldq, const void*
     }
     smem_set = 227 * 1024;
   }
-  dim3 grid(static_cast<unsigned>(static_cast<long long>(B) * HW), heads / wpb);
-  temporal_attn_kernel<<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  const int warps = hpb < 8 ? hpb : 8;
+  const dim3 grid(static_cast<unsigned>(static_cast<long long>(B) * HW), heads / hpb);
+  temporal_attn_kernel<<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(q), ldq, static_cast<const __half*>(k), ldk, static_cast<const __half*>(v), ldv,
-      static_cast<__half*>(o), ldo, T, HW, d, scale * 1.4426950408889634f);
+      static_cast<__half*>(o), ldo, T, HW, hpb, d, scale * 1.4426950408889634f);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_temporal_attention");
   return CCEDIT_OK;

@@ -34,25 +34,16 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
-// accumulate the 8 per-channel (sum, sumsq) of one thread into per-group shared accumulators
-__device__ __forceinline__ void flush_groups(const float (&s)[8], const float (&q)[8], int c0, int cpg, float* sg) {
-  int g = c0 / cpg;
-  float rs = 0.f, rq = 0.f;
+// Deterministic group reduction: every thread parks its 8 per-channel (sum, sumsq) in shared memory
+// ([slot][C] each), then one thread per (slot-set, group) adds them in a fixed order.  (Float atomics would make the
+// statistics - and through fp16 re-rounding the whole network output - differ from run to run.)
+__device__ __forceinline__ void park_channels(const float (&s)[8], const float (&q)[8], float* ssum, float* ssq, int slot,
+                                              int C, int c0) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int gj = (c0 + j) / cpg;
-    if (gj != g) {
-      atomicAdd(&sg[2 * g], rs);
-      atomicAdd(&sg[2 * g + 1], rq);
-      rs = 0.f;
-      rq = 0.f;
-      g = gj;
-    }
-    rs += s[j];
-    rq += q[j];
+    ssum[slot * C + c0 + j] = s[j];
+    ssq[slot * C + c0 + j] = q[j];
   }
-  atomicAdd(&sg[2 * g], rs);
-  atomicAdd(&sg[2 * g + 1], rq);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -61,10 +52,10 @@ __device__ __forceinline__ void flush_groups(const float (&s)[8], const float (&
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void gn_spatial_stats_kernel(const __half* __restrict__ x, float* __restrict__ partial, int HW, int C,
                                         int nvec, int rpi, int nsplit) {
-  __shared__ float sg[2 * kGroups];
+  extern __shared__ float gn_sm[];            // [2][rpi][C]
+  float* ssum = gn_sm;
+  float* ssq = gn_sm + rpi * C;
   const int f = blockIdx.y, split = blockIdx.x;
-  if (threadIdx.x < 2 * kGroups) sg[threadIdx.x] = 0.f;
-  __syncthreads();
   const int cv = threadIdx.x % nvec, r0 = threadIdx.x / nvec;
   const int rows_per_split = (HW + nsplit - 1) / nsplit;
   const int row_begin = split * rows_per_split;
@@ -82,10 +73,20 @@ __global__ void gn_spatial_stats_kernel(const __half* __restrict__ x, float* __r
       q[j] += v[j] * v[j];
     }
   }
-  flush_groups(s, q, cv * 8, C / kGroups, sg);
+  park_channels(s, q, ssum, ssq, r0, C, cv * 8);
   __syncthreads();
-  if (threadIdx.x < 2 * kGroups)
-    partial[(static_cast<size_t>(f) * nsplit + split) * 2 * kGroups + threadIdx.x] = sg[threadIdx.x];
+  if (threadIdx.x < kGroups) {
+    const int cpg = C / kGroups, g = threadIdx.x;
+    float ts = 0.f, tq = 0.f;
+    for (int r = 0; r < rpi; ++r)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        ts += ssum[r * C + c];
+        tq += ssq[r * C + c];
+      }
+    float* pp = partial + (static_cast<size_t>(f) * nsplit + split) * 2 * kGroups;
+    pp[2 * g] = ts;
+    pp[2 * g + 1] = tq;
+  }
 }
 
 // spatial GroupNorm: apply (+ optional SiLU). grid (nchunk, F)
@@ -144,11 +145,12 @@ __global__ void gn_spatial_apply_kernel(const __half* __restrict__ x, __half* __
 __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, int B, int T, int HW,
                                    int C, int nvec, int ppb, float eps, int silu) {
-  extern __shared__ float sg_dyn[];  // [ppb][64]
+  extern __shared__ float sg_dyn[];  // [2][ppb][C] per-channel sums, then [ppb][64] (mean, rstd) per group
+  float* ssum = sg_dyn;
+  float* ssq = sg_dyn + ppb * C;
+  float* sstat = sg_dyn + 2 * ppb * C;
   const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec;
   const long long pix = static_cast<long long>(blockIdx.x) * ppb + pl;  // over B*HW
-  for (int i = threadIdx.x; i < ppb * 2 * kGroups; i += blockDim.x) sg_dyn[i] = 0.f;
-  __syncthreads();
   const bool active = pix < static_cast<long long>(B) * HW;
   const int b = active ? static_cast<int>(pix / HW) : 0;
   const int hw = active ? static_cast<int>(pix % HW) : 0;
@@ -156,35 +158,48 @@ __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restr
   const uint4* xb = reinterpret_cast<const uint4*>(x) + (static_cast<size_t>(b) * T * HW + hw) * nvec + cv;
   uint4* yb = reinterpret_cast<uint4*>(y) + (static_cast<size_t>(b) * T * HW + hw) * nvec + cv;
   const int cpg = C / kGroups;
-  float* sg = sg_dyn + pl * 2 * kGroups;
-  if (active) {
+  {
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    for (int t = 0; t < T; ++t) {
-      float v[8];
-      unpack8(__ldg(xb + t * tstride), v);
+    if (active) {
+      for (int t = 0; t < T; ++t) {
+        float v[8];
+        unpack8(__ldg(xb + t * tstride), v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += v[j];
-        q[j] += v[j] * v[j];
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[j];
+          q[j] += v[j] * v[j];
+        }
       }
     }
-    flush_groups(s, q, cv * 8, cpg, sg);
+    park_channels(s, q, ssum, ssq, pl, C, cv * 8);
+  }
+  __syncthreads();
+  const float n = static_cast<float>(T) * static_cast<float>(cpg);
+  for (int idx = threadIdx.x; idx < ppb * kGroups; idx += blockDim.x) {
+    const int p = idx / kGroups, g = idx % kGroups;
+    float ts = 0.f, tq = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      ts += ssum[p * C + c];
+      tq += ssq[p * C + c];
+    }
+    const float mean = ts / n;
+    const float var = fmaxf(tq / n - mean * mean, 0.f);
+    sstat[p * 2 * kGroups + 2 * g] = mean;
+    sstat[p * 2 * kGroups + 2 * g + 1] = rsqrtf(var + eps);
   }
   __syncthreads();
   if (active) {
+    const float* sg = sstat + pl * 2 * kGroups;
     float sc[8], sh[8];
-    const float n = static_cast<float>(T) * static_cast<float>(cpg);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = cv * 8 + j;
       const int g = c / cpg;
-      const float mean = sg[2 * g] / n;
-      const float var = fmaxf(sg[2 * g + 1] / n - mean * mean, 0.f);
-      const float a = rsqrtf(var + eps) * gamma[c];
+      const float a = sg[2 * g + 1] * gamma[c];
       sc[j] = a;
-      sh[j] = beta[c] - mean * a;
+      sh[j] = beta[c] - sg[2 * g] * a;
     }
     for (int t = 0; t < T; ++t) {
       float v[8];
@@ -270,7 +285,7 @@ using namespace ccedit;
 extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gamma, const float* beta, float* partial,
                                         int32_t F, int32_t HW, int32_t C, float eps, int32_t silu, void* stream) {
   CCEDIT_CHECK_ARG(x && y && gamma && beta && partial, "ccedit_groupnorm_spatial: null pointer");
-  CCEDIT_CHECK_ARG(F > 0 && HW > 0 && C > 0 && C % kGroups == 0 && C % 8 == 0 && C <= 8192,
+  CCEDIT_CHECK_ARG(F > 0 && HW > 0 && C > 0 && C % kGroups == 0 && C % 8 == 0 && C <= 4096,
                    "ccedit_groupnorm_spatial: bad shape F=%d HW=%d C=%d (C must be a multiple of 32)", F, HW, C);
   const int nvec = C / 8, rpi = pick_rpi(nvec);
   const int threads = nvec * rpi;
@@ -279,8 +294,8 @@ extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gam
   if (nsplit < 1) nsplit = 1;
   if (nsplit > kMaxSplit) nsplit = kMaxSplit;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  gn_spatial_stats_kernel<<<dim3(nsplit, F), threads, 0, st>>>(static_cast<const __half*>(x), partial, HW, C, nvec, rpi,
-                                                               nsplit);
+  gn_spatial_stats_kernel<<<dim3(nsplit, F), threads, 2 * rpi * C * sizeof(float), st>>>(
+      static_cast<const __half*>(x), partial, HW, C, nvec, rpi, nsplit);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_spatial(stats)");
   int nchunk = static_cast<int>(bytes / 32768);
   if (nchunk < 1) nchunk = 1;
@@ -295,13 +310,13 @@ extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gam
 extern "C" int ccedit_groupnorm_temporal(const void* x, void* y, const float* gamma, const float* beta, int32_t B,
                                          int32_t T, int32_t HW, int32_t C, float eps, int32_t silu, void* stream) {
   CCEDIT_CHECK_ARG(x && y && gamma && beta, "ccedit_groupnorm_temporal: null pointer");
-  CCEDIT_CHECK_ARG(B > 0 && T > 0 && HW > 0 && C > 0 && C % kGroups == 0 && C % 8 == 0 && C <= 8192,
+  CCEDIT_CHECK_ARG(B > 0 && T > 0 && HW > 0 && C > 0 && C % kGroups == 0 && C % 8 == 0 && C <= 4096,
                    "ccedit_groupnorm_temporal: bad shape B=%d T=%d HW=%d C=%d", B, T, HW, C);
   const int nvec = C / 8, ppb = pick_rpi(nvec);
   const int threads = nvec * ppb;
   const long long npix = static_cast<long long>(B) * HW;
   const int grid = static_cast<int>((npix + ppb - 1) / ppb);
-  gn_temporal_kernel<<<grid, threads, ppb * 2 * kGroups * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  gn_temporal_kernel<<<grid, threads, (2 * ppb * C + ppb * 2 * kGroups) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, B, T, HW, C, nvec, ppb, eps, silu);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_temporal");

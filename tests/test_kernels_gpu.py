@@ -13,6 +13,9 @@ from conftest import assert_close
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-3, 1e-4
+# attention: the probabilities are rounded to fp16 for the P.V tensor-core product (as in every flash-attention kernel,
+# including the SDPA backend the reference hits on a GPU), which adds up to ~1.5e-4 absolute on outputs of magnitude 1
+ATOL_ATTN = 2e-4
 
 
 def close(got, ref, what, rtol=RTOL, atol=ATOL):
@@ -144,7 +147,7 @@ def test_attention(ops, Fr, L, Lkv, heads, d):
     q, k, v = rnd(Fr, L, C, seed=24), rnd(Fr, Lkv, C, seed=25), rnd(Fr, Lkv, C, seed=26)
     out = torch.empty(Fr, L, C, dtype=torch.float16, device="cuda")
     ops.attention(q.cuda(), [ops.KVSegment(k.cuda(), v.cuda())], heads, out)
-    close(out, _sdpa(q, k, v, heads), f"attention L={L} Lkv={Lkv} d={d}")
+    close(out, _sdpa(q, k, v, heads), f"attention L={L} Lkv={Lkv} d={d}", atol=ATOL_ATTN)
 
 
 def test_attention_text_keys_shared_by_frames(ops):
@@ -155,7 +158,7 @@ def test_attention_text_keys_shared_by_frames(ops):
     out = torch.empty(B * T, L, C, dtype=torch.float16, device="cuda")
     ops.attention(q.cuda(), [ops.KVSegment(k.cuda(), v.cuda(), div=T)], heads, out)
     ref = _sdpa(q, k.repeat_interleave(T, 0), v.repeat_interleave(T, 0), heads)
-    close(out, ref, "text attention")
+    close(out, ref, "text attention", atol=ATOL_ATTN)
 
 
 def test_attention_center_self_two_segments(ops):
@@ -168,10 +171,11 @@ def test_attention_center_self_two_segments(ops):
     ops.attention(q.cuda(), [ops.KVSegment(kc, vc, div=T, mul=T, add=T // 2), ops.KVSegment(kc, vc)], heads, out)
     ctr = lambda t: t.view(B, T, L, C)[:, T // 2].repeat_interleave(T, 0)
     ref = _sdpa(q, torch.cat([ctr(k), k], 1), torch.cat([ctr(v), v], 1), heads)
-    close(out, ref, "center_self attention")
+    close(out, ref, "center_self attention", atol=ATOL_ATTN)
 
 
-@pytest.mark.parametrize("B,T,HW,heads,d", [(2, 17, 50, 8, 40), (1, 9, 30, 8, 160), (2, 33, 20, 8, 80), (1, 1, 5, 8, 40)])
+@pytest.mark.parametrize("B,T,HW,heads,d", [(2, 17, 50, 8, 40), (1, 9, 30, 8, 160), (2, 33, 20, 8, 80), (1, 1, 5, 8, 40),
+                                           (1, 33, 6, 8, 160), (1, 40, 3, 4, 16)])
 def test_temporal_attention(ops, B, T, HW, heads, d):
     C = heads * d
     q, k, v = rnd(B, T, HW, C, seed=33), rnd(B, T, HW, C, seed=34), rnd(B, T, HW, C, seed=35)
