@@ -10,9 +10,11 @@
 #include "../../include/ccedit_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace ccedit {
 extern std::atomic<long long> g_launch_count;
+int attention_tc(const ccedit_attn_desc* a, cudaStream_t st);   // attention_tc.cu: tcgen05 path, -1 if not eligible
 
 constexpr int kFaBM = 128;     // queries per CTA (8 warps x 16 rows)
 constexpr int kFaBN = 64;      // keys per tile
@@ -393,6 +395,14 @@ extern "C" int ccedit_attention(const ccedit_attn_desc* a, void* stream) {
   p.d = a->d;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // head dims up to 64 (d = 40: 88 % of the attention FLOPs) run on tcgen05 / TMEM; CCEDIT_ATTN_LEGACY=1 forces the
+  // mma.sync kernel (A/B measurements only)
+  static const bool legacy = [] { const char* e = getenv("CCEDIT_ATTN_LEGACY"); return e && e[0] == '1'; }();
+  if (!legacy && (reinterpret_cast<uintptr_t>(a->q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0 &&
+      a->scale > 0.f) {
+    const int rc = attention_tc(a, st);
+    if (rc >= 0) return rc;
+  }
   if (a->d <= 16) return launch_fa<16>(p, a->frames, a->heads, st);
   if (a->d <= 32) return launch_fa<32>(p, a->frames, a->heads, st);
   if (a->d <= 48) return launch_fa<48>(p, a->frames, a->heads, st);

@@ -1,0 +1,57 @@
+"""Developer check + timing of ccedit_attention against torch SDPA on the GPU (NOT the parity suite)."""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ccedit_b200 import ops  # noqa: E402
+
+torch.manual_seed(0)
+dev = "cuda"
+
+
+def ref(q, k, v, heads):
+    Fq, L, C = q.shape
+    sp = lambda t: t.float().view(t.shape[0], t.shape[1], heads, C // heads).transpose(1, 2)
+    return F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(Fq, L, C)
+
+
+def check(Fr, L, Lkv, heads, d, scale=1.0):
+    C = heads * d
+    q, k, v = [(torch.randn(Fr, n, C, device=dev) * scale).half() for n in (L, Lkv, Lkv)]
+    out = torch.empty(Fr, L, C, dtype=torch.float16, device=dev)
+    ops.attention(q, [ops.KVSegment(k, v)], heads, out)
+    torch.cuda.synchronize()
+    r = ref(q, k, v, heads)
+    err = (out.float() - r).abs().max().item()
+    print(f"F={Fr} L={L} Lkv={Lkv} h={heads} d={d} scale={scale}: max|err|={err:.3e} max|ref|={r.abs().max().item():.3f} "
+          f"{'OK' if err < 2e-3 * max(1.0, r.abs().max().item()) else 'BAD'}", flush=True)
+
+
+def bench(Fr, L, heads, d, iters=5):
+    C = heads * d
+    qkv = torch.randn(Fr, L, 3 * C, device=dev).half()
+    out = torch.empty(Fr, L, C, dtype=torch.float16, device=dev)
+    run = lambda: ops.attention(qkv[..., :C], [ops.KVSegment(qkv[..., C:2 * C], qkv[..., 2 * C:])], heads, out)
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"attn F={Fr} L={L} d={d}: {ms:8.3f} ms  {4.0 * Fr * L * L * C / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    print("legacy" if os.environ.get("CCEDIT_ATTN_LEGACY") == "1" else "tcgen05", flush=True)
+    for args in [(1, 128, 128, 1, 40), (1, 256, 256, 2, 40), (2, 300, 77, 8, 40), (3, 384, 384, 8, 40), (2, 1000, 1000, 8, 40),
+                 (1, 6144, 6144, 8, 40), (2, 512, 512, 4, 64), (2, 200, 200, 4, 16), (1, 1, 1, 8, 40), (2, 640, 640, 8, 32)]:
+        check(*args)
+    check(2, 1024, 1024, 8, 40, scale=4.0)        # large logits: exercises the lazy rescaling
+    bench(34, 6144, 8, 40)
+    bench(34, 1536, 8, 40)
