@@ -70,6 +70,7 @@ SIGNATURES = {
     "ccedit_abi_version": (C.c_int, []),
     "ccedit_launch_count": (C.c_int64, []),
     "ccedit_gemm": (C.c_int, [C.POINTER(GemmDesc), _vp]),
+    "ccedit_gemm_trace": (C.c_int, [_vp]),
     "ccedit_groupnorm_spatial": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp]),
     "ccedit_groupnorm_temporal": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "ccedit_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),

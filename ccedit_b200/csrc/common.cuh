@@ -44,9 +44,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-// exact-erf GELU (torch F.gelu default, reference attention.py:120-122)
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// SiLU with the fast-division intrinsic (MUFU.RCP + FMUL, ~2 ulp): the IEEE '/' drags a slow-path call into every use
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// exact-erf GELU (torch F.gelu default, reference attention.py:120-122).
+// erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the fp16 rounding of the result):
+//   erf(z) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z >= 0
+__device__ __forceinline__ float erf_as_f(float x) {
+  const float z = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = __expf(-z * z);
+  return copysignf(fmaf(-poly, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752440f)); }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier
@@ -85,11 +99,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > CCEDIT_MBAR_SPIN_LIMIT) {
-      printf("ccedit: mbarrier timeout block(%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x,
-             parity);
-      __trap();
-    }
+    if (++spins > CCEDIT_MBAR_SPIN_LIMIT) __trap();   // surfaces as a launch failure instead of a hung GPU
   }
 }
 

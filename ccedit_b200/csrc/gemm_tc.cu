@@ -9,12 +9,17 @@
 // without any transposition (the reference makes three full-tensor copies per spatial_temporal_forward,
 // openaimodel.py:147,157,177).
 //
-// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (TMEM -> registers -> bias/emb/SiLU/GEGLU/residual -> fp16 global stores).
+// Roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..9 = epilogue, two warpgroups that split the 16-column chunks of a tile between them
+// (TMEM -> registers -> bias/emb/SiLU/GEGLU/residual -> fp16 global stores).  Everything the epilogue reads from
+// global memory for a tile (bias row into per-warp shared memory, this thread's residual segments into registers) is
+// issued BEFORE it waits for the accumulator, so those latencies overlap the tile's MMAs instead of serialising
+// behind them (measured: the un-prefetched epilogue held K=320 GEMMs at 10 % tensor-pipe activity).
 #include "common.cuh"
 #include "../../include/ccedit_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace ccedit {
@@ -25,7 +30,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                  // 64 fp16 = 128 B = one SWIZZLE_128B row
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
+constexpr int kEpiWarps = 8;                 // two epilogue warpgroups
+constexpr int kMaxChunks = 8;                // 16-column chunks per thread: 256 output columns / 16 / 2 groups
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;              // columns between the two accumulator buffers
 
@@ -51,6 +58,7 @@ struct GemmKParams {
   long long r2[4];
   int flags;
   uint32_t idesc;
+  long long* trace;   // diagnostics: per-tile phase clocks of CTA 0 (ccedit_gemm_trace), or nullptr
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -69,6 +77,15 @@ __device__ __forceinline__ void add_res16(float (&v)[16], const __half* p) {
     v[2 * j + 1] += f.y;
   }
 }
+__device__ __forceinline__ void add_res16(float (&v)[16], const uint4& a, const uint4& b) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    v[2 * j] += f.x;
+    v[2 * j + 1] += f.y;
+  }
+}
 __device__ __forceinline__ void add_f32x16(float (&v)[16], const float* p) {
   const float4* q = reinterpret_cast<const float4*>(p);
 #pragma unroll
@@ -81,6 +98,204 @@ __device__ __forceinline__ void add_f32x16(float (&v)[16], const float* p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue.  Measured with ccedit_gemm_trace: the epilogue is a serial instruction stream per warp (two warps per SM
+// sub-partition), its cost is instruction count and - above all - instruction-cache footprint (a fully unrolled
+// multi-mode epilogue spent > 60 % of every tile in fetch misses after taken branches).  Hence:
+//   * the kernel is a template on (MODE, NRES): each launch contains only the code of its own epilogue;
+//   * one compact ROLLED loop over 16-column chunks; the residual rows of chunk i+1 are requested while chunk i is
+//     being processed, those of the first chunk (and the bias row, staged in per-warp shared memory) before the
+//     wait on the MMAs of the tile;
+//   * tile coordinates advance by a mixed-radix add (no divisions), per-thread offsets are split into a
+//     thread-constant and a tile-uniform part.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kModePlain = 0, kModeGeglu = 1, kModeSilu = 2;
+
+__device__ __forceinline__ void ld_res(uint4 (&dst)[2], const __half* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  dst[0] = __ldg(q);
+  dst[1] = __ldg(q + 1);
+}
+__device__ __forceinline__ void add_res(float (&v)[16], const uint4 (&r)[2]) {
+  const uint32_t w[8] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    v[2 * j] += f.x;
+    v[2 * j + 1] += f.y;
+  }
+}
+
+template <int MODE, int NRES>
+__device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, float* sbias_all, int warp, int lane) {
+  constexpr bool GEGLU = MODE == kModeGeglu;
+  const int wq = warp & 3;            // TMEM lane quarter this warp may access
+  const int eg = (warp - 2) >> 2;     // epilogue group: takes the 16-column chunks with (chunk index & 1) == eg
+  const int row = wq * 32 + lane;
+  float* sbias = sbias_all + (warp - 2) * 256;
+  const int ncols_out = GEGLU ? p.bn / 2 : p.bn;
+  const int nchunks = ncols_out >> 4;
+
+  // thread-constant part of the coordinates / offsets
+  int l[4];
+  long long lo_o = 0, lo_r1 = 0, lo_r2 = 0;
+  {
+    int r = row;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      l[i] = r % p.box[i];
+      r /= p.box[i];
+      lo_o += static_cast<long long>(l[i]) * p.ostr[i];
+      if (NRES >= 1) lo_r1 += static_cast<long long>(l[i]) * p.r1[i];
+      if (NRES >= 2) lo_r2 += static_cast<long long>(l[i]) * p.r2[i];
+    }
+  }
+  // tile counter as mixed-radix digits (n_tile, t0..t3); the per-iteration increment gridDim.x likewise
+  int dig[5], inc[5], radix[5];
+  {
+    int t = blockIdx.x, g = gridDim.x;
+    radix[0] = p.n_tiles;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) radix[i + 1] = p.tiles[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      dig[i] = t % radix[i]; t /= radix[i];
+      inc[i] = g % radix[i]; g /= radix[i];
+    }
+  }
+  int as = 0;
+  uint32_t aphase = 0;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
+  int titer = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    if (tracing && titer < 64) p.trace[16 * titer + 0] = clock64();
+    const int n_tile = dig[0];
+    bool valid = true;
+    long long off_o = lo_o, off_r1 = lo_r1, off_r2 = lo_r2;
+    int rb_c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int base = dig[i + 1] * p.box[i];
+      valid = valid && (base + l[i] < p.odim[i]);
+      off_o += static_cast<long long>(base) * p.ostr[i];
+      if (NRES >= 1) off_r1 += static_cast<long long>(base) * p.r1[i];
+      if (NRES >= 2) off_r2 += static_cast<long long>(base) * p.r2[i];
+      if (i == p.rb_dim) rb_c = base + l[i];
+    }
+    const int col0_out = n_tile * ncols_out;
+    __half* optr = p.out + off_o + col0_out;
+    const __half* r1ptr = p.res1 + off_r1 + col0_out;   // dereferenced only if NRES >= 1 and valid
+    const __half* r2ptr = p.res2 + off_r2 + col0_out;
+
+    // ---- global reads of this tile, issued before the wait on its MMAs ----
+    uint4 c1[2], c2[2], n1[2], n2[2];
+    if (NRES >= 1 && valid && eg < nchunks) ld_res(c1, r1ptr + eg * 16);
+    if (NRES >= 2 && valid && eg < nchunks) ld_res(c2, r2ptr + eg * 16);
+    const float* rbptr = nullptr;
+    {
+      bool rb_uniform = false;
+      int rb_row = 0;
+      if (!GEGLU && p.rowbias) {
+        rb_row = p.rb_div == 1 ? rb_c : rb_c / p.rb_div;
+        rb_uniform = __all_sync(0xffffffffu, rb_row == __shfl_sync(0xffffffffu, rb_row, 0));
+        if (!rb_uniform && valid) rbptr = p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out;
+      }
+      float bv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {                      // bn <= 256: all loads in flight together
+        const int i = lane + 32 * k;
+        bv[k] = (p.bias && i < p.bn) ? __ldg(p.bias + n_tile * p.bn + i) : 0.f;
+        if (rb_uniform && i < p.bn) bv[k] += __ldg(p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out + i);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sbias[lane + 32 * k] = bv[k];
+    }
+    __syncwarp();
+    if (tracing && titer < 64) p.trace[16 * titer + 1] = clock64();
+
+    mbar_wait(&tfull_bar[as], aphase);
+    tcgen05_fence_after();
+    if (tracing && titer < 64) p.trace[16 * titer + 2] = clock64();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
+
+#pragma unroll 1
+    for (int ci = eg; ci < nchunks; ci += 2) {
+      const int c = ci * 16;
+      uint32_t r[16];
+      float v[16];
+      tmem_ld_32x32b_x16(taddr + c, r);
+      if (GEGLU) {
+        uint32_t g[16];
+        tmem_ld_32x32b_x16(taddr + ncols_out + c, g);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
+          const float4 bg = *reinterpret_cast<const float4*>(sbias + ncols_out + c + j);
+          v[j] = (__uint_as_float(r[j]) + bv.x) * gelu_erf_f(__uint_as_float(g[j]) + bg.x);
+          v[j + 1] = (__uint_as_float(r[j + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[j + 1]) + bg.y);
+          v[j + 2] = (__uint_as_float(r[j + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[j + 2]) + bg.z);
+          v[j + 3] = (__uint_as_float(r[j + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[j + 3]) + bg.w);
+        }
+      } else {
+        // request the residual rows of this thread's next chunk while this one is processed
+        if (NRES >= 1 && valid && ci + 2 < nchunks) ld_res(n1, r1ptr + c + 32);
+        if (NRES >= 2 && valid && ci + 2 < nchunks) ld_res(n2, r2ptr + c + 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
+          v[j] = __uint_as_float(r[j]) + bv.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + bv.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+        }
+      }
+      if (valid) {
+        if (rbptr) add_f32x16(v, rbptr + c);
+        if (MODE == kModeSilu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+        }
+        if (NRES >= 1) add_res(v, c1);
+        if (NRES >= 2) add_res(v, c2);
+        uint4 s0, s1;
+        s0.x = pack_half2(v[0], v[1]);
+        s0.y = pack_half2(v[2], v[3]);
+        s0.z = pack_half2(v[4], v[5]);
+        s0.w = pack_half2(v[6], v[7]);
+        s1.x = pack_half2(v[8], v[9]);
+        s1.y = pack_half2(v[10], v[11]);
+        s1.z = pack_half2(v[12], v[13]);
+        s1.w = pack_half2(v[14], v[15]);
+        uint4* o4 = reinterpret_cast<uint4*>(optr + c);
+        o4[0] = s0;
+        o4[1] = s1;
+      }
+      if (NRES >= 1) { c1[0] = n1[0]; c1[1] = n1[1]; }
+      if (NRES >= 2) { c2[0] = n2[0]; c2[1] = n2[1]; }
+    }
+    if (tracing && titer < 64) p.trace[16 * titer + 3] = clock64();
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    if (tracing && titer < 64) p.trace[16 * titer + 4] = clock64();
+    ++titer;
+    as ^= 1;
+    if (as == 0) aphase ^= 1u;
+    // next tile: mixed-radix add with carry
+    int carry = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      int d = dig[i] + inc[i] + carry;
+      carry = d >= radix[i] ? 1 : 0;
+      dig[i] = d - (carry ? radix[i] : 0);
+    }
+  }
+}
+
+template <int MODE, int NRES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmKParams p) {
@@ -94,6 +309,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [kEpiWarps][256] floats, 16 B aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,7 +323,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -160,13 +376,16 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      int mt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
         tcgen05_fence_after();
+        if (p.trace && blockIdx.x == 0 && mt < 64) p.trace[16 * mt + 5] = clock64();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccStride);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
+          if (kb == 0 && p.trace && blockIdx.x == 0 && mt < 64) p.trace[16 * mt + 7] = clock64();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
@@ -182,109 +401,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (p.trace && blockIdx.x == 0 && mt < 64) p.trace[16 * mt + 6] = clock64();
+        ++mt;
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
     }
   } else {
     // ===================== epilogue warps =====================
-    const int wq = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = wq * 32 + lane;
-    int as = 0;
-    uint32_t aphase = 0;
-    const bool geglu = (p.flags & CCEDIT_GEMM_GEGLU) != 0;
-    const bool do_silu = (p.flags & CCEDIT_GEMM_SILU) != 0;
-    const int ncols_out = geglu ? p.bn / 2 : p.bn;
-    // row -> local coordinates inside the tile box
-    int l[4];
-    {
-      int r = row;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        l[i] = r % p.box[i];
-        r /= p.box[i];
-      }
-    }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      int m = tile / p.n_tiles;
-      bool valid = true;
-      long long off_o = 0, off_r1 = 0, off_r2 = 0;
-      int rb_row = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = (m % p.tiles[i]) * p.box[i] + l[i];
-        m /= p.tiles[i];
-        valid = valid && (c < p.odim[i]);
-        off_o += static_cast<long long>(c) * p.ostr[i];
-        off_r1 += static_cast<long long>(c) * p.r1[i];
-        off_r2 += static_cast<long long>(c) * p.r2[i];
-        if (i == p.rb_dim) rb_row = c / p.rb_div;
-      }
-      const int col0_out = n_tile * ncols_out;
-      __half* optr = p.out + off_o + col0_out;
-      const __half* r1ptr = p.res1 ? p.res1 + off_r1 + col0_out : nullptr;
-      const __half* r2ptr = p.res2 ? p.res2 + off_r2 + col0_out : nullptr;
-      const float* rbptr = p.rowbias ? p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out : nullptr;
-
-      mbar_wait(&tfull_bar[as], aphase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
-
-      for (int c = 0; c < ncols_out; c += 16) {
-        uint32_t r[16];
-        float v[16];
-        tmem_ld_32x32b_x16(taddr + c, r);
-        if (geglu) {
-          uint32_t g[16];
-          tmem_ld_32x32b_x16(taddr + ncols_out + c, g);
-          tmem_ld_wait();
-          float gv[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v[j] = __uint_as_float(r[j]);
-            gv[j] = __uint_as_float(g[j]);
-          }
-          if (p.bias) {
-            add_f32x16(v, p.bias + n_tile * p.bn + c);
-            add_f32x16(gv, p.bias + n_tile * p.bn + ncols_out + c);
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= gelu_erf_f(gv[j]);
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) add_f32x16(v, p.bias + n_tile * p.bn + c);
-        }
-        if (valid) {
-          if (rbptr) add_f32x16(v, rbptr + c);
-          if (do_silu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
-          }
-          if (r1ptr) add_res16(v, r1ptr + c);
-          if (r2ptr) add_res16(v, r2ptr + c);
-          uint4 s0, s1;
-          s0.x = pack_half2(v[0], v[1]);
-          s0.y = pack_half2(v[2], v[3]);
-          s0.z = pack_half2(v[4], v[5]);
-          s0.w = pack_half2(v[6], v[7]);
-          s1.x = pack_half2(v[8], v[9]);
-          s1.y = pack_half2(v[10], v[11]);
-          s1.z = pack_half2(v[12], v[13]);
-          s1.w = pack_half2(v[14], v[15]);
-          uint4* o4 = reinterpret_cast<uint4*>(optr + c);
-          o4[0] = s0;
-          o4[1] = s1;
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      as ^= 1;
-      if (as == 0) aphase ^= 1u;
-    }
+    epilogue_loop<MODE, NRES>(p, tmem_base, tfull_bar, tempty_bar, sbias_all, warp, lane);
   }
 
   tcgen05_fence_before();
@@ -324,6 +449,21 @@ int device_sm_count() {
   return sms;
 }
 
+static long long* g_gemm_trace = nullptr;
+
+template <int MODE, int NRES>
+static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
+                               int smem_bytes, cudaStream_t stream) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tap_gemm_kernel<MODE, NRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  tap_gemm_kernel<MODE, NRES><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  return cudaGetLastError();
+}
+
 static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   CCEDIT_CHECK_ARG(d != nullptr, "ccedit_gemm: null descriptor");
   CCEDIT_CHECK_ARG(d->a && d->w && d->out, "ccedit_gemm: null a/w/out pointer");
@@ -335,6 +475,9 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   CCEDIT_CHECK_ARG(d->a_dims[0] % 8 == 0, "ccedit_gemm: C=%d must be a multiple of 8", d->a_dims[0]);
   const bool geglu = (d->flags & CCEDIT_GEMM_GEGLU) != 0;
   CCEDIT_CHECK_ARG(!geglu || d->bn % 32 == 0, "ccedit_gemm: GEGLU needs bn %% 32 == 0 (bn=%d)", d->bn);
+  CCEDIT_CHECK_ARG(!(geglu && d->rowbias), "ccedit_gemm: GEGLU and rowbias cannot be combined");
+  CCEDIT_CHECK_ARG(!(geglu && (d->flags & CCEDIT_GEMM_SILU)), "ccedit_gemm: GEGLU and SiLU cannot be combined");
+  CCEDIT_CHECK_ARG(!(geglu && (d->res1 || d->res2)), "ccedit_gemm: GEGLU and residuals cannot be combined");
   long long boxprod = 1;
   for (int i = 0; i < 4; ++i) {
     CCEDIT_CHECK_ARG(d->box[i] >= 1 && d->box[i] <= 256, "ccedit_gemm: box[%d]=%d", i, d->box[i]);
@@ -415,35 +558,50 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.res1 = static_cast<const __half*>(d->res1);
   p.res2 = static_cast<const __half*>(d->res2);
   p.flags = d->flags;
+  { const char* e = getenv("CCEDIT_GEMM_DEV"); if (e) p.flags |= atoi(e) << 8; }   // developer experiments only
   p.idesc = umma_idesc_f16(kBlockM, d->bn);
+  p.trace = g_gemm_trace;
   const int stage_bytes = kABytes + d->bn * kBlockK * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (192 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + 1024 + 512;
+  const int smem_bytes = stages * stage_bytes + 1024 + 512 + kEpiWarps * 256 * 4;
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) {
-    set_last_error("ccedit_gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-    return CCEDIT_ERR_CUDA;
-  }
   const int sms = device_sm_count();
   if (sms <= 0) {
     set_last_error("ccedit_gemm: no CUDA device");
     return CCEDIT_ERR_CUDA;
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  tap_gemm_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  const int nres = (d->res1 ? 1 : 0) + (d->res2 ? 1 : 0);
+  if (d->res2 && !d->res1) {
+    p.res1 = p.res2;
+    for (int i = 0; i < 4; ++i) p.r1[i] = p.r2[i];
+    p.res2 = nullptr;
+  }
+  cudaError_t err;
+  if (geglu) err = launch_gemm<kModeGeglu, 0>(tmA, tmB, p, grid, smem_bytes, stream);
+  else if (d->flags & CCEDIT_GEMM_SILU) {
+    CCEDIT_CHECK_ARG(nres == 0, "ccedit_gemm: SiLU and residuals cannot be combined");
+    err = launch_gemm<kModeSilu, 0>(tmA, tmB, p, grid, smem_bytes, stream);
+  } else if (nres == 0) err = launch_gemm<kModePlain, 0>(tmA, tmB, p, grid, smem_bytes, stream);
+  else if (nres == 1) err = launch_gemm<kModePlain, 1>(tmA, tmB, p, grid, smem_bytes, stream);
+  else err = launch_gemm<kModePlain, 2>(tmA, tmB, p, grid, smem_bytes, stream);
+  if (err != cudaSuccess) {
+    set_last_error("ccedit_gemm: launch failed: %s", cudaGetErrorString(err));
+    return CCEDIT_ERR_CUDA;
+  }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_gemm");
   return CCEDIT_OK;
 }
 
 }  // namespace ccedit
+
+extern "C" int ccedit_gemm_trace(int64_t* device_buf) {
+  ccedit::g_gemm_trace = reinterpret_cast<long long*>(device_buf);
+  return CCEDIT_OK;
+}
 
 extern "C" int ccedit_gemm(const ccedit_gemm_desc* d, void* stream) {
   return ccedit::gemm_impl(d, static_cast<cudaStream_t>(stream));

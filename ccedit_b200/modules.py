@@ -67,12 +67,12 @@ class ParamHolder(nn.Module):
             self._cache[key] = c = (ver, make())
         return c[1]
 
-    def packed(self, device, geglu=False, scale: float = 1.0) -> PackedWeight:
+    def packed(self, device, geglu=False, scale: float = 1.0, max_bn: int = 256) -> PackedWeight:
         def make():
             w = self.weight if scale == 1.0 else self.weight.detach().float() * scale
             b = self.bias if (scale == 1.0 or self.bias is None) else self.bias.detach().float() * scale
-            return ops.pack_weight(w, b, device, geglu=geglu)
-        return self._cached((device, "w", geglu, scale), make)
+            return ops.pack_weight(w, b, device, geglu=geglu, max_bn=max_bn)
+        return self._cached((device, "w", geglu, scale, max_bn), make)
 
     def affine(self, device):
         return self._cached((device, "affine"), lambda: (

@@ -33,6 +33,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # per-launch profiler (bench.py --breakdown / roofline): when enabled every C-ABI call is bracketed by CUDA events on
 # the launching stream and recorded with its algorithmic FLOPs and bytes
 _PROF = None
+_PROF_SHAPES = False     # developer switch: split the gemm classes by problem shape (tools/gemm_shapes.py)
 
 
 def profile_start() -> None:
@@ -73,10 +74,10 @@ def _require(t: torch.Tensor, dtype=torch.float16, name="tensor"):
 # ---------------------------------------------------------------------------------------------------------------------
 # weights
 # ---------------------------------------------------------------------------------------------------------------------
-def pick_bn(n: int, geglu: bool = False) -> int:
-    """Largest N tile (multiple of 16, <= 256; multiple of 32 for GEGLU) that divides n."""
+def pick_bn(n: int, geglu: bool = False, max_bn: int = 256) -> int:
+    """Largest N tile (multiple of 16, <= max_bn <= 256; multiple of 32 for GEGLU) that divides n."""
     step = 32 if geglu else 16
-    for bn in range(256, 0, -step):
+    for bn in range(max_bn - max_bn % step, 0, -step):
         if n % bn == 0:
             return bn
     raise ValueError(f"output width {n} is not a multiple of {step}")
@@ -101,7 +102,7 @@ class PackedWeight:
 
 
 def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor], device, geglu: bool = False, n_pad_to: int = 16,
-                cin_pad_to: int = 8) -> PackedWeight:
+                cin_pad_to: int = 8, max_bn: int = 256) -> PackedWeight:
     """w: [N, Cin, *taps] in the reference (PyTorch) layout: Linear [N,K], Conv2d [N,Cin,kh,kw], Conv1d [N,Cin,kt].
 
     Tap order is row-major over the kernel dims (kh*3+kw / kt), matching ``conv_taps``/``temporal_taps``.
@@ -118,7 +119,7 @@ def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor], device, geglu: bo
         w = torch.cat([w, w.new_zeros(n_p - n, ntaps, cin)], 0)
         if b is not None:
             b = torch.cat([b, b.new_zeros(n_p - n)], 0)
-    bn = pick_bn(n_p, geglu)
+    bn = pick_bn(n_p, geglu, max_bn)
     if geglu:
         half = n_p // 2
         hb = bn // 2
@@ -259,6 +260,8 @@ def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = 
     kind = {1: "gemm.linear", 3: "gemm.temporal_k3", 9: "gemm.conv3x3"}.get(len(taps), "gemm.other")
     if pw.geglu:
         kind = "gemm.linear_geglu"
+    if _PROF_SHAPES:
+        kind += f"[M={m_rows},K={pw.ntaps}x{min(c, pw.k)},N={pw.n},bn={pw.bn},res={int(res1 is not None) + int(res2 is not None)}]"
     _call(kind, _lib.load().ccedit_gemm, (C.byref(d), _stream()), flops=2.0 * m_rows * pw.ntaps * min(c, pw.k) * pw.n,
           nbytes=_nb(a, pw.w, out, res1, res2))
     return out

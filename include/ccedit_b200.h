@@ -82,6 +82,11 @@ typedef struct ccedit_gemm_desc {
 } ccedit_gemm_desc;
 
 int ccedit_gemm(const ccedit_gemm_desc* d, void* stream);
+/* Diagnostics: while device_buf (int64 [64][16], device memory) is set, CTA 0 of every ccedit_gemm launch records the
+ * SM clock at its per-tile phases: [0] epilogue tile start, [1] epilogue global reads issued, [2] accumulator ready,
+ * [3] stores issued, [4] accumulator released, [5] MMA warp owns the accumulator, [6] MMAs issued, [7] first operands
+ * landed, [8..11] first 32-column block: TMEM load issued / returned / math done / stored.  NULL switches it off.  Used by tools/dev_gemm.py; never set on the product path. */
+int ccedit_gemm_trace(int64_t* device_buf);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Normalisation (fp32 statistics, fp16 in/out).
