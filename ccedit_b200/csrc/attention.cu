@@ -248,27 +248,22 @@ static int launch_fa(const FaParams& p, int frames, int heads, cudaStream_t st) 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// temporal attention: one CTA per pixel, one warp per head, one lane per query frame.
+// temporal attention: one CTA per pixel (x head group), one warp per head.
 //   phase 1: the CTA streams the pixel's q, k, v rows ([T][C], C = heads*d contiguous) into shared memory with
-//            16-byte cp.async (fully coalesced rows, everything in flight at once: this kernel is HBM-bound);
-//   phase 2: lane i of warp h holds query frame i of head h: scores against all T keys (K rows are read as
-//            warp-wide broadcasts), softmax in registers / a per-warp scratch column, P.V in 8-channel chunks.
-// Row stride in smem is C+8 halves so that the per-lane q reads (different rows) are bank-conflict free.
+//            16-byte cp.async (fully coalesced rows, everything in flight at once; rows T..TK-1 are zero-filled);
+//   phase 2: warp h computes softmax(Q_h K_h^T) V_h for its head with warp-level tensor-core MMAs (m16n8k16): the T x T
+//            problem is tiny (T <= 64), so the scalar version of this kernel was instruction-bound (7 TFLOP/s, 830 GB/s);
+//            with ~150 warp instructions per (pixel, head) it is bound by the HBM stream of q, k, v, o again.
+// Row stride in smem is C+8 halves (odd multiple of 16 B): conflict-free ldmatrix.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-    f[2 * j] = t.x;
-    f[2 * j + 1] = t.y;
-  }
-}
-
-__global__ void temporal_attn_kernel(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k,
-                                     long long ldk, const __half* __restrict__ v, long long ldv, __half* __restrict__ o,
-                                     long long ldo, int T, int HW, int heads, int d, float scale_log2) {
+template <int DP, int TK>   // DP: head dim rounded up (multiple of 16); TK: keys rounded up to 32 or 64
+__global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __restrict__ q, long long ldq,
+                                                            const __half* __restrict__ k, long long ldk,
+                                                            const __half* __restrict__ v, long long ldv,
+                                                            __half* __restrict__ o, long long ldo, int T, int HW, int heads,
+                                                            int d, float scale_log2) {
   // `heads` = heads handled by this CTA (a head group when T*C does not fit in shared memory); blockIdx.y = group
+  constexpr int KSTEPS = DP / 16, NT_O = DP / 8, NTK = TK / 8;
   extern __shared__ __align__(16) uint8_t ta_smem[];
   const int C = heads * d;
   const long long col0 = static_cast<long long>(blockIdx.y) * C;
@@ -277,84 +272,156 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ q, long long ldq
   v += col0;
   o += col0;
   const int RS = C + 8;                                   // smem row stride (halves)
-  __half* sq = reinterpret_cast<__half*>(ta_smem);        // [T][RS]
-  __half* sk = sq + static_cast<size_t>(T) * RS;
-  __half* sv = sk + static_cast<size_t>(T) * RS;
-  float* sp = reinterpret_cast<float*>(sv + static_cast<size_t>(T) * RS);  // [heads][T][32] scores / probabilities
+  __half* sq = reinterpret_cast<__half*>(ta_smem);        // [TK][RS]
+  __half* sk = sq + TK * RS;
+  __half* sv = sk + TK * RS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long pix = blockIdx.x;                       // b*HW + hw
   const int b = static_cast<int>(pix / HW), hw = static_cast<int>(pix % HW);
   const long long row0 = (static_cast<long long>(b) * T) * HW + hw;  // row of frame 0; frame t adds t*HW
   const int cpr = C >> 3;                                 // 16-byte chunks per row
-  for (int i = threadIdx.x; i < T * cpr; i += blockDim.x) {
+  for (int i = threadIdx.x; i < TK * cpr; i += blockDim.x) {
     const int t = i / cpr, c = i - t * cpr;
-    const long long row = row0 + static_cast<long long>(t) * HW;
-    cp_async_16(smem_u32(sq + t * RS + c * 8), q + row * ldq + c * 8, true);
-    cp_async_16(smem_u32(sk + t * RS + c * 8), k + row * ldk + c * 8, true);
-    cp_async_16(smem_u32(sv + t * RS + c * 8), v + row * ldv + c * 8, true);
+    const bool ok = t < T;
+    const long long row = row0 + static_cast<long long>(ok ? t : 0) * HW;
+    cp_async_16(smem_u32(sq + t * RS + c * 8), q + row * ldq + c * 8, ok);
+    cp_async_16(smem_u32(sk + t * RS + c * 8), k + row * ldk + c * 8, ok);
+    cp_async_16(smem_u32(sv + t * RS + c * 8), v + row * ldv + c * 8, ok);
   }
+  // the 8 padding halves at the end of every row feed the last k-step of the last head: keep them finite
+  for (int i = threadIdx.x; i < 3 * TK; i += blockDim.x)
+    *reinterpret_cast<uint4*>(sq + i * RS + C) = make_uint4(0, 0, 0, 0);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
 
-  const int nchunk = d >> 3;
+  const bool mask_tail = (d & 15) != 0;                   // d % 16 == 8: the last k-step covers 8 foreign channels
   for (int head = warp; head < heads; head += (blockDim.x >> 5)) {
-    float* spw = sp + static_cast<size_t>(head) * T * 32;
-    for (int i0 = 0; i0 < T; i0 += 32) {
-      const int i = i0 + lane;
-      const bool act = i < T;
-      const __half* qi = sq + (act ? i : 0) * RS + head * d;
-      // ---- scores ----
-      float m = -INFINITY;
-      for (int j = 0; j < T; ++j) {
-        const __half* kj = sk + j * RS + head * d;
-        float s = 0.f;
-        for (int c = 0; c < nchunk; ++c) {
-          float a[8], bb[8];
-          unpack8h(*reinterpret_cast<const uint4*>(qi + c * 8), a);
-          unpack8h(*reinterpret_cast<const uint4*>(kj + c * 8), bb);
+    const __half* hq = sq + head * d;
+    const __half* hk = sk + head * d;
+    const __half* hv = sv + head * d;
+    for (int m0 = 0; m0 < T; m0 += 16) {
+      // ---- S = Q K^T for 16 query frames x TK keys ----
+      float sacc[NTK][4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) s = fmaf(a[e], bb[e], s);
-        }
-        s *= scale_log2;
-        spw[j * 32 + lane] = s;
-        m = fmaxf(m, s);
-      }
-      float l = 0.f;
-      for (int j = 0; j < T; ++j) {
-        const float p = exp2f(spw[j * 32 + lane] - m);
-        spw[j * 32 + lane] = p;
-        l += p;
-      }
-      const float inv = 1.f / l;
-      // ---- O = P V, 8 channels at a time ----
-      __half* op = o + (row0 + static_cast<long long>(act ? i : 0) * HW) * ldo + head * d;
-      for (int c = 0; c < nchunk; ++c) {
-        float acc[8];
+      for (int i = 0; i < NTK; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        for (int j = 0; j < T; ++j) {
-          const float p = spw[j * 32 + lane];
-          float vv[8];
-          unpack8h(*reinterpret_cast<const uint4*>(sv + j * RS + head * d + c * 8), vv);
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        if (ks * 16 >= d) break;                                   // DP may exceed d by whole k-steps (e.g. d = 96)
+        uint32_t qf[4];
+        ldmatrix_x4(qf, smem_u32(hq + (m0 + (lane & 15)) * RS + ks * 16 + (lane >> 4) * 8));
+        if (mask_tail && d - ks * 16 == 8) qf[2] = qf[3] = 0u;     // zero the 8 channels past d
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vv[e], acc[e]);
-        }
-        if (act) {
-          uint4 u;
-          __half2 h0 = __floats2half2_rn(acc[0] * inv, acc[1] * inv), h1 = __floats2half2_rn(acc[2] * inv, acc[3] * inv);
-          __half2 h2 = __floats2half2_rn(acc[4] * inv, acc[5] * inv), h3 = __floats2half2_rn(acc[6] * inv, acc[7] * inv);
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2);
-          u.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(op + c * 8) = u;
+        for (int np = 0; np < NTK / 2; ++np) {
+          uint32_t kf[4];
+          ldmatrix_x4(kf, smem_u32(hk + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * RS + ks * 16 + ((lane >> 3) & 1) * 8));
+          const uint32_t b0[2] = {kf[0], kf[1]}, b1[2] = {kf[2], kf[3]};
+          mma_m16n8k16(sacc[2 * np], qf, b0);
+          mma_m16n8k16(sacc[2 * np + 1], qf, b1);
         }
       }
-      __syncwarp();
+      // ---- softmax over the T valid keys (rows g and g+8 of the fragment) ----
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < NTK; ++nt) {
+        const int col = nt * 8 + (lane & 3) * 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float val = (col + (e & 1)) < T ? sacc[nt][e] * scale_log2 : -INFINITY;
+          sacc[nt][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+        mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      }
+      float rs[2] = {0.f, 0.f};
+      uint32_t pf[NTK / 2][4];
+#pragma unroll
+      for (int nt = 0; nt < NTK; ++nt) {
+        const float p0 = exp2f(sacc[nt][0] - mx[0]), p1 = exp2f(sacc[nt][1] - mx[0]);
+        const float p2 = exp2f(sacc[nt][2] - mx[1]), p3 = exp2f(sacc[nt][3] - mx[1]);
+        rs[0] += p0 + p1;
+        rs[1] += p2 + p3;
+        __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+        pf[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&h01);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&h23);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        rs[h] += __shfl_xor_sync(0xffffffffu, rs[h], 1);
+        rs[h] += __shfl_xor_sync(0xffffffffu, rs[h], 2);
+      }
+      // ---- O = P V ----
+      float oacc[NT_O][4];
+#pragma unroll
+      for (int i = 0; i < NT_O; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < NTK / 2; ++kk) {
+#pragma unroll
+        for (int np = 0; np < NT_O / 2; ++np) {
+          if (np * 16 >= d) break;                                 // DP may exceed d by whole 16-column groups
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, smem_u32(hv + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS + np * 16 + (lane >> 4) * 8));
+          const uint32_t b0[2] = {vf[0], vf[1]}, b1[2] = {vf[2], vf[3]};
+          mma_m16n8k16(oacc[2 * np], pf[kk], b0);
+          mma_m16n8k16(oacc[2 * np + 1], pf[kk], b1);
+        }
+      }
+      const float inv0 = 1.f / rs[0], inv1 = 1.f / rs[1];
+      const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
+      __half* o0 = o + (row0 + static_cast<long long>(r0) * HW) * ldo + head * d;
+      __half* o1 = o + (row0 + static_cast<long long>(r1) * HW) * ldo + head * d;
+#pragma unroll
+      for (int nt = 0; nt < NT_O; ++nt) {
+        const int col = nt * 8 + (lane & 3) * 2;
+        if (col < d) {
+          if (r0 < T) *reinterpret_cast<__half2*>(o0 + col) = __floats2half2_rn(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+          if (r1 < T) *reinterpret_cast<__half2*>(o1 + col) = __floats2half2_rn(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+        }
+      }
     }
   }
+}
+
+template <int DP, int TK>
+static int launch_ta(const __half* q, long long ldq, const __half* k, long long ldk, const __half* v, long long ldv, __half* o,
+                     long long ldo, int B, int T, int HW, int heads, int d, float scale_log2, cudaStream_t st) {
+  int hpb = heads;   // heads per CTA: all of them unless the pixel's q/k/v rows do not fit in shared memory
+  auto smem_for = [&](int h) { return static_cast<size_t>(3) * TK * (h * d + 8) * 2; };
+  while (hpb > 1 && (smem_for(hpb) > 200 * 1024 || heads % hpb != 0)) --hpb;
+  const size_t smem = smem_for(hpb);
+  CCEDIT_CHECK_ARG(smem <= 227 * 1024, "ccedit_temporal_attention: T*d too large for shared memory (%zu bytes)", smem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel<DP, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_last_error("ccedit_temporal_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CCEDIT_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  const int warps = hpb < 8 ? hpb : 8;
+  const dim3 grid(static_cast<unsigned>(static_cast<long long>(B) * HW), heads / hpb);
+  temporal_attn_kernel<DP, TK><<<grid, warps * 32, smem, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, T, HW, hpb, d, scale_log2);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_temporal_attention");
+  return CCEDIT_OK;
+}
+
+template <int TK>
+static int dispatch_ta(const __half* q, long long ldq, const __half* k, long long ldk, const __half* v, long long ldv,
+                       __half* o, long long ldo, int B, int T, int HW, int heads, int d, float sl, cudaStream_t st) {
+  if (d <= 16) return launch_ta<16, TK>(q, ldq, k, ldk, v, ldv, o, ldo, B, T, HW, heads, d, sl, st);
+  if (d <= 32) return launch_ta<32, TK>(q, ldq, k, ldk, v, ldv, o, ldo, B, T, HW, heads, d, sl, st);
+  if (d <= 48) return launch_ta<48, TK>(q, ldq, k, ldk, v, ldv, o, ldo, B, T, HW, heads, d, sl, st);
+  if (d <= 64) return launch_ta<64, TK>(q, ldq, k, ldk, v, ldv, o, ldo, B, T, HW, heads, d, sl, st);
+  if (d <= 80) return launch_ta<80, TK>(q, ldq, k, ldk, v, ldv, o, ldo, B, T, HW, heads, d, sl, st);
+  if (d <= 128) return launch_ta<128, TK>(q, ldq, k, ldk, v, ldv, o, ldo, B, T, HW, heads, d, sl, st);
+  return launch_ta<160, TK>(q, ldq, k, ldk, v, ldv, o, ldo, B, T, HW, heads, d, sl, st);
 }
 
 }  // namespace ccedit
@@ -416,33 +483,20 @@ extern "C" int ccedit_temporal_attention(const void* q, int64_t ldq, const void*
                                          int64_t ldv, void* o, int64_t ldo, int32_t B, int32_t T, int32_t HW,
                                          int32_t heads, int32_t d, float scale, void* stream) {
   CCEDIT_CHECK_ARG(q && k && v && o, "ccedit_temporal_attention: null pointer");
-  CCEDIT_CHECK_ARG(B > 0 && T > 0 && T <= 64 && HW > 0 && heads > 0 && d > 0 && d % 8 == 0,
-                   "ccedit_temporal_attention: bad shape B=%d T=%d HW=%d heads=%d d=%d (T<=64, d%%8==0)", B, T, HW, heads, d);
+  CCEDIT_CHECK_ARG(B > 0 && T > 0 && T <= 64 && HW > 0 && heads > 0 && d > 0 && d % 8 == 0 && d <= 160,
+                   "ccedit_temporal_attention: bad shape B=%d T=%d HW=%d heads=%d d=%d (T<=64, d%%8==0, d<=160)", B, T, HW,
+                   heads, d);
   CCEDIT_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
                    "ccedit_temporal_attention: row strides must be multiples of 8 elements");
   CCEDIT_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                      reinterpret_cast<uintptr_t>(o)) & 15) == 0,
                    "ccedit_temporal_attention: q/k/v/o must be 16-byte aligned");
-  int hpb = heads;   // heads per CTA: all of them unless the pixel's q/k/v rows do not fit in shared memory
-  auto smem_for = [&](int h) { return static_cast<size_t>(3) * T * (h * d + 8) * 2 + static_cast<size_t>(h) * T * 32 * 4; };
-  while (hpb > 1 && (smem_for(hpb) > 200 * 1024 || heads % hpb != 0)) --hpb;
-  const size_t smem = smem_for(hpb);
-  CCEDIT_CHECK_ARG(smem <= 227 * 1024, "ccedit_temporal_attention: T*d too large for shared memory (%zu bytes)", smem);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem_set == 0) {
-    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      set_last_error("ccedit_temporal_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return CCEDIT_ERR_CUDA;
-    }
-    smem_set = 227 * 1024;
-  }
-  const int warps = hpb < 8 ? hpb : 8;
-  const dim3 grid(static_cast<unsigned>(static_cast<long long>(B) * HW), heads / hpb);
-  temporal_attn_kernel<<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(q), ldq, static_cast<const __half*>(k), ldk, static_cast<const __half*>(v), ldv,
-      static_cast<__half*>(o), ldo, T, HW, hpb, d, scale * 1.4426950408889634f);
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_temporal_attention");
-  return CCEDIT_OK;
+  const __half* qp = static_cast<const __half*>(q);
+  const __half* kp = static_cast<const __half*>(k);
+  const __half* vp = static_cast<const __half*>(v);
+  __half* op = static_cast<__half*>(o);
+  const float sl = scale * 1.4426950408889634f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (T <= 32) return dispatch_ta<32>(qp, ldq, kp, ldk, vp, ldv, op, ldo, B, T, HW, heads, d, sl, st);
+  return dispatch_ta<64>(qp, ldq, kp, ldk, vp, ldv, op, ldo, B, T, HW, heads, d, sl, st);
 }

@@ -215,49 +215,59 @@ __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per token row, two-pass statistics on register-resident data. C <= 32*8*kLnVecs.
+// LayerNorm: one warp per token row, two-pass statistics on register-resident data.  Templated on the number of
+// 16-byte vectors per lane (C <= 256 * NV) so that the narrow rows of the big levels (C = 320: NV = 2) do not pay the
+// register footprint of the widest ones - occupancy is what hides the HBM latency of this kernel - and every warp
+// works on two rows at a time to double the bytes in flight.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kLnVecs = 10;  // up to C = 2560
-__global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta, long long M, int C,
-                                 float eps) {
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        long long M, int C, float eps) {
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
+  if (row0 >= M) return;
   const int nvec = C >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
-  float v[kLnVecs][8];
-  float s = 0.f;
+  const bool two = row0 + 1 < M;
+  float v[2][NV][8];
 #pragma unroll
-  for (int i = 0; i < kLnVecs; ++i) {
-    const int iv = lane + 32 * i;
-    if (iv < nvec) {
-      unpack8(__ldg(xr + iv), v[i]);
+  for (int r = 0; r < 2; ++r) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (row0 + (r && two ? 1 : 0)) * ldx);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
+    for (int i = 0; i < NV; ++i) {
+      const int iv = lane + 32 * i;
+      if (iv < nvec) unpack8(__ldg(xr + iv), v[r][i]);
     }
   }
+  float mean[2], rstd[2];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / static_cast<float>(C);
-  float q = 0.f;
+  for (int r = 0; r < 2; ++r) {
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnVecs; ++i) {
-    const int iv = lane + 32 * i;
-    if (iv < nvec) {
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dlt = v[i][j] - mean;
-        q += dlt * dlt;
+        for (int j = 0; j < 8; ++j) s += v[r][i][j];
       }
-    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean[r] = s / static_cast<float>(C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dlt = v[r][i][j] - mean[r];
+          q += dlt * dlt;
+        }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd[r] = rsqrtf(q / static_cast<float>(C) + eps);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
-  uint4* yr = reinterpret_cast<uint4*>(y + row * static_cast<long long>(C));
-#pragma unroll
-  for (int i = 0; i < kLnVecs; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int iv = lane + 32 * i;
     if (iv < nvec) {
       const float4* g4 = reinterpret_cast<const float4*>(gamma + iv * 8);
@@ -265,10 +275,15 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, long long ldx, __
       const float4 ga = __ldg(g4), gb = __ldg(g4 + 1), ba = __ldg(b4), bb = __ldg(b4 + 1);
       const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
       const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-      float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + be[j];
-      yr[iv] = pack8(o);
+      for (int r = 0; r < 2; ++r) {
+        if (r == 0 || two) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (v[r][i][j] - mean[r]) * rstd[r] * gg[j] + be[j];
+          reinterpret_cast<uint4*>(y + (row0 + r) * static_cast<long long>(C))[iv] = pack8(o);
+        }
+      }
     }
   }
 }
@@ -326,12 +341,23 @@ extern "C" int ccedit_groupnorm_temporal(const void* x, void* y, const float* ga
 extern "C" int ccedit_layernorm(const void* x, int64_t ldx, void* y, const float* gamma, const float* beta, int64_t M,
                                 int32_t C, float eps, void* stream) {
   CCEDIT_CHECK_ARG(x && y && gamma && beta, "ccedit_layernorm: null pointer");
-  CCEDIT_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0 && C <= 32 * 8 * kLnVecs && ldx % 8 == 0,
-                   "ccedit_layernorm: bad shape M=%lld C=%d ldx=%lld", (long long)M, C, (long long)ldx);
+  CCEDIT_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0 && C <= 2560 && ldx % 8 == 0,
+                   "ccedit_layernorm: bad shape M=%lld C=%d ldx=%lld (C %% 8 == 0, C <= 2560)", (long long)M, C, (long long)ldx);
   const int wpb = 8;
-  const long long grid = (M + wpb - 1) / wpb;
-  layernorm_kernel<<<static_cast<unsigned>(grid), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), ldx, static_cast<__half*>(y), gamma, beta, M, C, eps);
+  const long long grid = (M + 2 * wpb - 1) / (2 * wpb);
+  const dim3 g(static_cast<unsigned>(grid));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __half* xp = static_cast<const __half*>(x);
+  __half* yp = static_cast<__half*>(y);
+  const int nv = (C / 8 + 31) / 32;
+  switch (nv) {
+    case 1: layernorm_kernel<1><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
+    case 2: layernorm_kernel<2><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
+    case 3: layernorm_kernel<3><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
+    case 4:
+    case 5: layernorm_kernel<5><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
+    default: layernorm_kernel<10><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
+  }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_layernorm");
   return CCEDIT_OK;
