@@ -9,6 +9,7 @@
 namespace ccedit {
 
 std::atomic<long long> g_launch_count{0};
+long long* g_trace_buf = nullptr;   // diagnostics buffer set by ccedit_gemm_trace (tap-GEMM and tcgen05 attention)
 
 static thread_local char g_err[1024] = "";
 

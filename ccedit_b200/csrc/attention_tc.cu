@@ -4,11 +4,13 @@
 // One CTA = 256 query rows (two 128-row tiles, each with its own softmax warpgroup) of one (frame, head):
 //   warp 0      TMA producer: K and V tiles [128 keys x 64 channels] through 3-D tensor maps (SWIZZLE_128B; rows past the
 //               end of the segment are zero-filled by TMA), 3-stage mbarrier ring
-//   warp 1      TMEM allocator + the single tcgen05.mma issuing lane:
+//   warp 1      TMEM allocator + tcgen05.mma issue (the whole converged warp runs the issue code with warp-uniform
+//               operands and one elected lane issues: from inside `if (lane == 0)` every tcgen05 instruction costs an
+//               ELECT / R2UR.BROADCAST / branch loop of ~100 clocks, which made this warp the bottleneck):
 //                 S_q  = Q_q . K_j^T      (A, B from shared memory, K-major, fp32 accumulator in TMEM)
 //                 O_q += P_q . V_j        (A = P from TMEM, B = V from shared memory, MN-major)
 //   warps 2-5   softmax of query tile 0 (thread = one query row = one TMEM lane): tcgen05.ld S -> running max with
-//   warps 6-9   lazy rescaling -> exp2 -> fp16 P written back over S with tcgen05.st -> row sums; final O / l epilogue
+//   warps 6-9   lazy rescaling -> exp2 -> fp16 P written to TMEM with tcgen05.st -> row sums; final O / l epilogue
 // The two query tiles share every K/V tile and interleave on the tensor pipe: while one tile is in its softmax the
 // other one's QK^T / PV run.  The kernel is bound by the MUFU exp2 rate (160 tensor FLOPs per exponential at d = 40).
 //
@@ -27,7 +29,10 @@ constexpr int kTcThreads = 320;
 constexpr int kTcTile = 128;                 // query rows per tile / keys per tile
 constexpr int kTcStages = 3;
 constexpr int kTcTileBytes = 128 * 128;      // [128 rows][64 halves], SWIZZLE_128B
-constexpr uint32_t kTcColS0 = 0, kTcColS1 = 128, kTcColO0 = 256, kTcColO1 = 320;
+// TMEM columns (all 512): S_q fp32 scores (128 keys), P_q the probabilities as packed fp16 (64 columns), O_q fp32 output.
+// P does not alias S: QK^T of the next key tile is issued into S_q right behind P.V, and a later MMA writing columns that
+// an earlier MMA still reads as its A operand is not a documented interlock.
+constexpr uint32_t kTcColS0 = 0, kTcColS1 = 128, kTcColP0 = 256, kTcColP1 = 320, kTcColO0 = 384, kTcColO1 = 448;
 
 struct FaTcParams {
   const __half* q;
@@ -44,6 +49,14 @@ struct FaTcParams {
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_warp(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
@@ -154,8 +167,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < ntiles; ++j) {
@@ -164,9 +177,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
         const int kvf = (f / p.kv_div[seg]) * p.kv_mul[seg] + p.kv_add[seg];
         mbar_wait(&kv_empty[stage], phase ^ 1u);
         uint8_t* sK = sKV + stage * 2 * kTcTileBytes;
-        mbar_arrive_expect_tx(&kv_full[stage], 2u * kTcTileBytes);
-        tma_load_3d(sK, seg == 0 ? &tmK0 : &tmK1, &kv_full[stage], head * d, k0, kvf);
-        tma_load_3d(sK + kTcTileBytes, seg == 0 ? &tmV0 : &tmV1, &kv_full[stage], head * d, k0, kvf);
+        mbar_arrive_expect_tx_warp(&kv_full[stage], 2u * kTcTileBytes);
+        tma_load_3d_warp(sK, seg == 0 ? &tmK0 : &tmK1, &kv_full[stage], head * d, k0, kvf);
+        tma_load_3d_warp(sK + kTcTileBytes, seg == 0 ? &tmV0 : &tmV1, &kv_full[stage], head * d, k0, kvf);
         if (++stage == kTcStages) {
           stage = 0;
           phase ^= 1u;
@@ -174,12 +187,13 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole converged warp; one elected lane issues, see umma_*_warp) ==========
+    {
       const uint32_t idesc_s = umma_idesc_f16(128, 128);
       const uint32_t idesc_o = umma_idesc_f16(128, NO) | (1u << 16);       // B (= V) is MN-major
       const uint32_t tS[2] = {tmem_base + kTcColS0, tmem_base + kTcColS1};
       const uint32_t tO[2] = {tmem_base + kTcColO0, tmem_base + kTcColO1};
+      const uint32_t tP[2] = {tmem_base + kTcColP0, tmem_base + kTcColP1};
       const uint64_t dQ[2] = {umma_desc_k_sw128(smem_u32(sQ)), umma_desc_k_sw128(smem_u32(sQ + kTcTileBytes))};
       mbar_wait(q_full, 0);
       fence_proxy_async_smem();
@@ -190,8 +204,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
         const uint64_t dK = umma_desc_k_sw128(smem_u32(sKV));
         for (int q = 0; q < nq; ++q) {
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks) umma_f16_ss(tS[q], dQ[q] + 2u * ks, dK + 2u * ks, idesc_s, ks ? 1u : 0u);
-          umma_commit(&s_full[q]);
+          for (int ks = 0; ks < KSTEPS; ++ks) umma_f16_ss_warp(tS[q], dQ[q] + 2u * ks, dK + 2u * ks, idesc_s, ks ? 1u : 0u);
+          umma_commit_warp(&s_full[q]);
         }
       }
       int stage = 0;
@@ -215,14 +229,14 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
           tcgen05_fence_after();
 #pragma unroll
           for (int kk = 0; kk < kTcTile / 16; ++kk)     // 16 keys per step: P columns +8, V rows +16 (2 KiB)
-            umma_f16_ts(tO[q], tS[q] + 8u * kk, dV + 128u * kk, idesc_o, (j | kk) ? 1u : 0u);
+            umma_f16_ts_warp(tO[q], tP[q] + 8u * kk, dV + 128u * kk, idesc_o, (j | kk) ? 1u : 0u);
           if (more) {
 #pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks) umma_f16_ss(tS[q], dQ[q] + 2u * ks, dKn + 2u * ks, idesc_s, ks ? 1u : 0u);
+            for (int ks = 0; ks < KSTEPS; ++ks) umma_f16_ss_warp(tS[q], dQ[q] + 2u * ks, dKn + 2u * ks, idesc_s, ks ? 1u : 0u);
           }
-          umma_commit(&s_full[q]);                      // S_q(j+1) ready / final: O_q complete
+          umma_commit_warp(&s_full[q]);                      // S_q(j+1) ready / final: O_q complete
         }
-        umma_commit(&kv_empty[stage]);                  // K_j, V_j no longer needed
+        umma_commit_warp(&kv_empty[stage]);                  // K_j, V_j no longer needed
         stage = nstage;
         phase = nphase;
       }
@@ -253,6 +267,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
       const uint32_t tS = tmem_base + lane_off + (qt ? kTcColS1 : kTcColS0);
       const uint32_t tO = tmem_base + lane_off + (qt ? kTcColO1 : kTcColO0);
+      const uint32_t tP = tmem_base + lane_off + (qt ? kTcColP1 : kTcColP0);
       const float c = p.scale_log2;
       float mref = -INFINITY, l = 0.f;
       for (int j = 0; j < ntiles; ++j) {
@@ -317,7 +332,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
             pk[i >> 1] = pack_h2(p0, p1);
             pk[(i >> 1) + 1] = pack_h2(p2, p3);
           }
-          tmem_st_x16(tS + (cc >> 1), pk);               // P (fp16 pairs) over the already-consumed S columns
+          tmem_st_x16(tP + (cc >> 1), pk);               // P as packed fp16 pairs
         }
         l += (s0 + s1) + (s2 + s3);
         tmem_st_wait();

@@ -339,73 +339,70 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int kblocks = p.ntaps * p.kchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        int m = tile / p.n_tiles;
-        int o[4];
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m = tile / p.n_tiles;
+      int o[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          o[i] = (m % p.tiles[i]) * p.box[i];
-          m /= p.tiles[i];
-        }
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int c1 = o[0] + p.taps[tap][0], c2 = o[1] + p.taps[tap][1];
-          const int c3 = o[2] + p.taps[tap][2], c4 = o[3] + p.taps[tap][3];
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sa = smem + stage * stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBlockK, c1, c2, c3, c4);
-            tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], (tap * p.kchunks + kc) * kBlockK, n_tile * p.bn);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
+      for (int i = 0; i < 4; ++i) {
+        o[i] = (m % p.tiles[i]) * p.box[i];
+        m /= p.tiles[i];
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      int mt = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1u);
-        tcgen05_fence_after();
-        if (p.trace && blockIdx.x == 0 && mt < 64) p.trace[16 * mt + 5] = clock64();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccStride);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          if (kb == 0 && p.trace && blockIdx.x == 0 && mt < 64) p.trace[16 * mt + 7] = clock64();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in 16-byte units
-            umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int c1 = o[0] + p.taps[tap][0], c2 = o[1] + p.taps[tap][1];
+        const int c3 = o[2] + p.taps[tap][2], c4 = o[3] + p.taps[tap][3];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * stage_bytes;
+          mbar_arrive_expect_tx_warp(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+          tma_load_5d_warp(sa, &tmA, &full_bar[stage], kc * kBlockK, c1, c2, c3, c4);
+          tma_load_2d_warp(sa + kABytes, &tmB, &full_bar[stage], (tap * p.kchunks + kc) * kBlockK, n_tile * p.bn);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
-        if (p.trace && blockIdx.x == 0 && mt < 64) p.trace[16 * mt + 6] = clock64();
-        ++mt;
-        as ^= 1;
-        if (as == 0) aphase ^= 1u;
       }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    int mt = 0;
+    const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tcgen05_fence_after();
+      if (tr && mt < 64) p.trace[16 * mt + 5] = clock64();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccStride);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (kb == 0 && tr && mt < 64) p.trace[16 * mt + 7] = clock64();
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint64_t adesc = umma_desc_k_sw128(sa);
+        const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in 16-byte units
+          umma_f16_ss_warp(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_warp(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit_warp(&tfull_bar[as]);  // accumulator complete -> epilogue
+      if (tr && mt < 64) p.trace[16 * mt + 6] = clock64();
+      ++mt;
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
     }
   } else {
     // ===================== epilogue warps =====================
@@ -449,7 +446,7 @@ int device_sm_count() {
   return sms;
 }
 
-static long long* g_gemm_trace = nullptr;
+extern long long* g_trace_buf;
 
 template <int MODE, int NRES>
 static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
@@ -560,7 +557,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.flags = d->flags;
   { const char* e = getenv("CCEDIT_GEMM_DEV"); if (e) p.flags |= atoi(e) << 8; }   // developer experiments only
   p.idesc = umma_idesc_f16(kBlockM, d->bn);
-  p.trace = g_gemm_trace;
+  p.trace = g_trace_buf;
   const int stage_bytes = kABytes + d->bn * kBlockK * 2;
   int stages = (192 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -599,7 +596,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
 }  // namespace ccedit
 
 extern "C" int ccedit_gemm_trace(int64_t* device_buf) {
-  ccedit::g_gemm_trace = reinterpret_cast<long long*>(device_buf);
+  ccedit::g_trace_buf = reinterpret_cast<long long*>(device_buf);
   return CCEDIT_OK;
 }
 

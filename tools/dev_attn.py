@@ -47,7 +47,24 @@ def bench(Fr, L, heads, d, iters=5):
     print(f"attn F={Fr} L={L} d={d}: {ms:8.3f} ms  {4.0 * Fr * L * L * C / ms / 1e9:8.1f} TFLOP/s", flush=True)
 
 
+def trace():
+    from ccedit_b200 import _lib
+    buf = torch.zeros(64, 16, dtype=torch.int64, device=dev)
+    _lib.load().ccedit_gemm_trace(buf.data_ptr())
+    bench(34, 6144, 8, 40, iters=1)
+    _lib.load().ccedit_gemm_trace(None)
+    t = buf.cpu()
+    t0 = int(t[0, 0])
+    print("tile: start s_ready ld_done math_done st_done barrier issued  (clocks since start; deltas)")
+    for i in range(2, 26):
+        r = [int(x) - t0 for x in t[i, :7]]
+        print(f"{i:3d}: {r[0]:7d} wait={r[1]-r[0]:5d} ld={r[2]-r[1]:5d} math={r[3]-r[2]:5d} st={r[4]-r[3]:5d} bar={r[5]-r[4]:5d} issue={r[6]-r[5]:5d} | tile={r[6]-r[0]:6d}")
+
+
 if __name__ == "__main__":
+    if os.environ.get("CCEDIT_ATTN_TRACE"):
+        trace()
+        sys.exit(0)
     print("legacy" if os.environ.get("CCEDIT_ATTN_LEGACY") == "1" else "tcgen05", flush=True)
     for args in [(1, 128, 128, 1, 40), (1, 256, 256, 2, 40), (2, 300, 77, 8, 40), (3, 384, 384, 8, 40), (2, 1000, 1000, 8, 40),
                  (1, 6144, 6144, 8, 40), (2, 512, 512, 4, 64), (2, 200, 200, 4, 16), (1, 1, 1, 8, 40), (2, 640, 640, 8, 32)]:
