@@ -236,6 +236,21 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+def ncu_traffic(kernel):
+    """Average DRAM bytes (read + write) per launch of `kernel`, from the committed ncu capture of one network call at
+    this workload (profiles/traffic.json, written by tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum`); None if no capture is committed for this kernel."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    ent = t.get("kernels", {}).get(kernel)
+    return None if ent is None else {"bytes_per_launch": ent["bytes_per_launch"], "launches": ent["launches"],
+                                     "algorithmic_bytes_per_launch": ent.get("algorithmic_bytes_per_launch"),
+                                     "source": t.get("source")}
+
+
 def kernel_breakdown(wrap, x_d, c_d, uc_d, peaks, dev):
     from ccedit_b200 import ops
     cc = {k: torch.cat((uc_d[k], c_d[k]), 0) for k in c_d}
@@ -271,6 +286,8 @@ def kernel_breakdown(wrap, x_d, c_d, uc_d, peaks, dev):
         f[1] += agg[r["kernel"]][1]
         f[2] += agg[r["kernel"]][3]
     top, (n, fl, ms) = max(fam.items(), key=lambda kv: kv[1][2])
+    top_bytes = sum(agg[r["kernel"]][2] for r in rows if (r["kernel"].startswith("gemm.") and top == "tap_gemm_kernel")
+                    or r["kernel"] == top)
     tensor_bound = fl > 0
     if tensor_bound:
         achieved = fl / ms / 1e9
@@ -281,7 +298,8 @@ def kernel_breakdown(wrap, x_d, c_d, uc_d, peaks, dev):
         achieved = by / ms / 1e6
         roof = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm"], 4)}
-    roof.update({"traffic": None, "launches_per_network_call": n, "avg_launch_ms": round(ms / n, 4),
+    roof.update({"traffic": ncu_traffic(top), "algorithmic_bytes_per_launch": round(top_bytes / n),
+                 "algorithmic_flop_per_launch": round(fl / n), "launches_per_network_call": n, "avg_launch_ms": round(ms / n, 4),
                  "share_of_network_call": round(ms / total_ms, 4),
                  "peak_source": f"MEASURED_PEAKS.json ({peaks['source']}; sustained figure: kernel timed inside a full "
                                 "network call)",

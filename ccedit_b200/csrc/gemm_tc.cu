@@ -181,7 +181,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
       off_o += static_cast<long long>(base) * p.ostr[i];
       if (NRES >= 1) off_r1 += static_cast<long long>(base) * p.r1[i];
       if (NRES >= 2) off_r2 += static_cast<long long>(base) * p.r2[i];
-      if (i == p.rb_dim) rb_c = base + l[i];
+      if (i == p.rb_dim) rb_c = min(base + l[i], p.odim[i] - 1);   // clamp: rows of the tile padding must not index past rowbias
     }
     const int col0_out = n_tile * ncols_out;
     __half* optr = p.out + off_o + col0_out;

@@ -64,7 +64,23 @@ __global__ void gn_spatial_stats_kernel(const __half* __restrict__ x, float* __r
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const uint4* base = reinterpret_cast<const uint4*>(x + static_cast<size_t>(f) * HW * C) + cv;
-  for (int r = row_begin + r0; r < row_end; r += rpi) {
+  int r = row_begin + r0;
+  for (; r + 3 * rpi < row_end; r += 4 * rpi) {          // four independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(base + static_cast<size_t>(r + k * rpi) * nvec);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      unpack8(u[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] += v[j] * v[j];
+      }
+    }
+  }
+  for (; r < row_end; r += rpi) {
     float v[8];
     unpack8(__ldg(base + static_cast<size_t>(r) * nvec), v);
 #pragma unroll
@@ -126,7 +142,24 @@ __global__ void gn_spatial_apply_kernel(const __half* __restrict__ x, __half* __
   const int row_end = min(HW, row_begin + rows_per_chunk);
   const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(f) * HW * C) + cv;
   uint4* yb = reinterpret_cast<uint4*>(y + static_cast<size_t>(f) * HW * C) + cv;
-  for (int r = row_begin + r0; r < row_end; r += rpi) {
+  int r = row_begin + r0;
+  for (; r + 3 * rpi < row_end; r += 4 * rpi) {          // four independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(xb + static_cast<size_t>(r + k * rpi) * nvec);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      unpack8(u[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = v[j] * sc[j] + sh[j];
+        v[j] = silu ? silu_f(t) : t;
+      }
+      yb[static_cast<size_t>(r + k * rpi) * nvec] = pack8(v);
+    }
+  }
+  for (; r < row_end; r += rpi) {
     float v[8];
     unpack8(__ldg(xb + static_cast<size_t>(r) * nvec), v);
 #pragma unroll
@@ -163,7 +196,23 @@ __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     if (active) {
-      for (int t = 0; t < T; ++t) {
+      int t = 0;
+      for (; t + 3 < T; t += 4) {                          // four frames in flight per thread
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(xb + (t + k) * tstride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v[8];
+          unpack8(u[k], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s[j] += v[j];
+            q[j] += v[j] * v[j];
+          }
+        }
+      }
+      for (; t < T; ++t) {
         float v[8];
         unpack8(__ldg(xb + t * tstride), v);
 #pragma unroll
@@ -201,7 +250,24 @@ __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restr
       sc[j] = a;
       sh[j] = beta[c] - sg[2 * g] * a;
     }
-    for (int t = 0; t < T; ++t) {
+    int t = 0;
+    for (; t + 3 < T; t += 4) {
+      uint4 u4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u4[k] = __ldg(xb + (t + k) * tstride);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v[8];
+        unpack8(u4[k], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float u = v[j] * sc[j] + sh[j];
+          v[j] = silu ? silu_f(u) : u;
+        }
+        yb[(t + k) * tstride] = pack8(v);
+      }
+    }
+    for (; t < T; ++t) {
       float v[8];
       unpack8(__ldg(xb + t * tstride), v);
 #pragma unroll

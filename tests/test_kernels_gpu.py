@@ -74,6 +74,20 @@ def test_conv3x3(ops, Fr, H, W, Cin, Cout, emb, silu):
     close(out[..., :Cout].permute(0, 3, 1, 2), ref, f"conv3x3 {Cin}->{Cout}")
 
 
+def test_conv3x3_time_embedding_rows_with_padded_tiles(ops):
+    """34 frames of 2x2 pixels: the 128-row tiles pad the frame axis to 64, and the padded rows must not index past the
+    [B, Cout] time-embedding rows (regression: an out-of-bounds read in the epilogue's bias staging)."""
+    Fr, T, H, W, C = 34, 17, 2, 2, 64
+    x, w = rnd(Fr, C, H, W, seed=50), rnd(C, C, 3, 3, seed=51, scale=1 / math.sqrt(9 * C))
+    b = rnd(C, seed=52).float()
+    pw = ops.pack_weight(w.float(), b, "cuda")
+    rb = rnd(Fr // T, C, seed=53).float()
+    out = torch.empty(Fr, H, W, C, dtype=torch.float16, device="cuda")
+    ops.gemm(x.permute(0, 2, 3, 1).contiguous().cuda(), pw, out, ops.conv_taps(), rowbias=rb.cuda(), rb_dim=2, rb_div=T)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1) + rb.repeat_interleave(T, 0)[:, :, None, None]
+    close(out.permute(0, 3, 1, 2), ref, "conv3x3 + time-embedding rows, padded frame axis")
+
+
 @pytest.mark.parametrize("Fr,H,W,C", [(2, 16, 24, 64), (3, 64, 96, 320), (2, 8, 12, 1280), (2, 32, 48, 16)])
 def test_conv3x3_stride2(ops, Fr, H, W, C):
     x, w = rnd(Fr, C, H, W, seed=9), rnd(C, C, 3, 3, seed=10, scale=1 / math.sqrt(9 * C))
