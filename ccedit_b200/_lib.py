@@ -86,6 +86,7 @@ SIGNATURES = {
     "ccedit_add_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp]),
     "ccedit_add_center_frame": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "ccedit_to_half": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "ccedit_hint_stem01": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

@@ -282,7 +282,18 @@ class ControlNet2D(UNetModel):
     def _hint_stem(self, hint_cl: torch.Tensor) -> torch.Tensor:
         g = hint_cl                                               # [F, H, W, 8]
         dev = g.device
+        first = 0
+        h0, h1 = self.input_hint_block[0], self.input_hint_block[2]
+        if (g.shape[-1] == 8 and tuple(h0.weight.shape[:1]) == (16,) and h0.weight.shape[1] <= 8
+                and tuple(h1.weight.shape[:2]) == (16, 16)):
+            # the two full-resolution layers (3 -> 16 -> 16) in one pass over the hint video (csrc/hint_stem.cu)
+            w0, b0 = h0._cached((dev, "hs0"), lambda: ops.pack_hint_stem_weight(h0.weight, h0.bias, dev, 8, 80))
+            w1, b1 = h1._cached((dev, "hs1"), lambda: ops.pack_hint_stem_weight(h1.weight, h1.bias, dev, 16, 144))
+            g = ops.hint_stem01(g, w0, b0, w1, b1)
+            first = 2
         for i, s in enumerate(self.HINT_STRIDES):
+            if i < first:
+                continue
             pw = self.input_hint_block[2 * i].packed(dev)
             F, H, W, _ = g.shape
             if s == 2:

@@ -11,8 +11,13 @@
 //                 O_q += P_q . V_j        (A = P from TMEM, B = V from shared memory, MN-major)
 //   warps 2-5   softmax of query tile 0 (thread = one query row = one TMEM lane): tcgen05.ld S -> running max with
 //   warps 6-9   lazy rescaling -> exp2 -> fp16 P written to TMEM with tcgen05.st -> row sums; final O / l epilogue
-// The two query tiles share every K/V tile and interleave on the tensor pipe: while one tile is in its softmax the
-// other one's QK^T / PV run.  The kernel is bound by the MUFU exp2 rate (160 tensor FLOPs per exponential at d = 40).
+// The two query tiles share every K/V tile and interleave on the tensor pipe.  The kernel is bound by the MUFU exp2 rate
+// (160 tensor FLOPs per exponential at d = 40), so everything is arranged to keep the softmax warps busy:
+//   * S_q(j+1) = Q_q K_{j+1}^T is issued as soon as the softmax warpgroup has pulled S_q(j) into registers (s_free), not
+//     after P_q(j): the MMA round trip is off the softmax -> softmax critical path (it used to be ~40 % of a tile);
+//   * the wait for P_q(j-1).V_{j-1} (o_done: P and O are free again) sits right before the first P store of tile j;
+//   * row maxima with 3-input max, and EMU of every 4 exponentials evaluated on the FMA pipe (Cody-Waite + degree-3
+//     polynomial, rel. error 8.8e-5, below the fp16 rounding of P) instead of MUFU.EX2.
 //
 // Replaces F.scaled_dot_product_attention (attention.py:444-448) for spatial self-attention, text cross-attention and
 // the two-segment centre+self context of SpatialTransformer3DCA (attention.py:1323-1336).
@@ -20,19 +25,28 @@
 #include "../../include/ccedit_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace ccedit {
 extern std::atomic<long long> g_launch_count;
+extern long long* g_trace_buf;
 
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 352;
+constexpr int kTcMmaWarp1 = 10;              // second MMA-issuing warp (query tile 1)
 constexpr int kTcTile = 128;                 // query rows per tile / keys per tile
 constexpr int kTcStages = 3;
+constexpr int kTcDefaultStagger = 2;
+constexpr int kTcDefaultEmu = 0;             // exponentials per group of 4 evaluated on the FMA pipe
 constexpr int kTcTileBytes = 128 * 128;      // [128 rows][64 halves], SWIZZLE_128B
 // TMEM columns (all 512): S_q fp32 scores (128 keys), P_q the probabilities as packed fp16 (64 columns), O_q fp32 output.
 // P does not alias S: QK^T of the next key tile is issued into S_q right behind P.V, and a later MMA writing columns that
 // an earlier MMA still reads as its A operand is not a documented interlock.
 constexpr uint32_t kTcColS0 = 0, kTcColS1 = 128, kTcColP0 = 256, kTcColP1 = 320, kTcColO0 = 384, kTcColO1 = 448;
+// Head dims <= 48 leave 32 columns free: O_1 moves down to 432 and the first 32 keys of P (16 columns) get a second
+// buffer per query tile, used on odd key tiles - the softmax warps can then start writing P(j+1) while P(j).V is still
+// running (the wait for it moves from the first to the second 32-key block; clock trace: ~400 clocks per tile).
+constexpr uint32_t kTcColO1Small = 432, kTcColX0 = 480, kTcColX1 = 496;
 
 struct FaTcParams {
   const __half* q;
@@ -44,6 +58,8 @@ struct FaTcParams {
   int ntile[2];
   int lq, d;
   float scale_log2;
+  int stagger;
+  long long* trace;   // diagnostics (ccedit_gemm_trace): per-tile phase clocks of CTA 0, or nullptr
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -102,6 +118,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// named barriers (ids 1, 2) hand the "exponential phase" back and forth between the two softmax warpgroups
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float max3_f(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+// 2^x on the FMA pipe: x = n + f (n = floor(x) by a round-down add of 1.5 * 2^23, f in [0, 1)), 2^f by a degree-3
+// minimax polynomial (max rel. error 8.8e-5), n added into the exponent field.  x is clamped to >= -126 (result ~1e-38,
+// which rounds to a zero probability); masked scores (-inf) take this path safely.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  float xr;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xr) : "f"(x), "f"(12582912.f));
+  const float f = x - (xr - 12582912.f);
+  float p = fmaf(0.077119089663028717041015625f, f, 0.227564394474029541015625f);
+  p = fmaf(p, f, 0.695146143436431884765625f);
+  p = fmaf(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(xr) << 23));
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -118,12 +159,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
-template <int KSTEPS>  // head dim d <= 16*KSTEPS (KSTEPS in 1..4); output tile width NO = 16*KSTEPS columns
+template <int KSTEPS, int EMU>  // head dim d <= 16*KSTEPS (KSTEPS in 1..4); output tile width NO = 16*KSTEPS columns
 __global__ void __launch_bounds__(kTcThreads, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                      const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
                      const __grid_constant__ FaTcParams p) {
   constexpr int NO = 16 * KSTEPS;
+  constexpr bool kPx = NO <= 48;             // second buffer for the first 32-key block of P (see kTcColX0)
   extern __shared__ uint8_t fa_smem_raw[];
   const uint32_t raw_addr = smem_u32(fa_smem_raw);
   uint8_t* smem = fa_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -135,7 +177,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
   uint64_t* s_full = bars + 2 * kTcStages;               // [2]  S_q ready (also: all earlier MMAs of tile q done)
   uint64_t* p_full = s_full + 2;                         // [2]  P_q written
   uint64_t* q_full = p_full + 2;                         // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 1);
+  uint64_t* s_free = q_full + 1;                         // [2]  S_q has been read into registers
+  uint64_t* o_done = s_free + 2;                         // [2]  P_q.V done: O_q consistent, P_q may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * kTcTile), head = blockIdx.y, f = blockIdx.z;
@@ -148,11 +192,13 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
     tma_prefetch_desc(&tmV0);
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], nq);
     }
     for (int q = 0; q < 2; ++q) {
       mbar_init(&s_full[q], 1);
       mbar_init(&p_full[q], 128);
+      mbar_init(&s_free[q], 128);
+      mbar_init(&o_done[q], 1);
     }
     mbar_init(q_full, 256);
     fence_barrier_init();
@@ -186,15 +232,19 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole converged warp; one elected lane issues, see umma_*_warp) ==========
-    {
+  } else if (warp == 1 || warp == kTcMmaWarp1) {
+    // ===================== MMA issuers: warp 1 serves query tile 0, warp 10 query tile 1 =====================
+    // (whole converged warp; one elected lane issues, see umma_*_warp).  One issuer per query tile: with a single warp
+    // serving both tiles in a fixed order, a tile's P.V had to wait behind the other tile's barriers (clock trace).
+    const int q = warp == 1 ? 0 : 1;
+    if (q < nq) {
       const uint32_t idesc_s = umma_idesc_f16(128, 128);
       const uint32_t idesc_o = umma_idesc_f16(128, NO) | (1u << 16);       // B (= V) is MN-major
-      const uint32_t tS[2] = {tmem_base + kTcColS0, tmem_base + kTcColS1};
-      const uint32_t tO[2] = {tmem_base + kTcColO0, tmem_base + kTcColO1};
-      const uint32_t tP[2] = {tmem_base + kTcColP0, tmem_base + kTcColP1};
-      const uint64_t dQ[2] = {umma_desc_k_sw128(smem_u32(sQ)), umma_desc_k_sw128(smem_u32(sQ + kTcTileBytes))};
+      const uint32_t tS = tmem_base + (q ? kTcColS1 : kTcColS0);
+      const uint32_t tO = tmem_base + (q ? (kPx ? kTcColO1Small : kTcColO1) : kTcColO0);
+      const uint32_t tP = tmem_base + (q ? kTcColP1 : kTcColP0);
+      const uint32_t tPx = tmem_base + (q ? kTcColX1 : kTcColX0);
+      const uint64_t dQ = umma_desc_k_sw128(smem_u32(sQ + q * kTcTileBytes));
       mbar_wait(q_full, 0);
       fence_proxy_async_smem();
       tcgen05_fence_after();
@@ -202,41 +252,41 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
       tcgen05_fence_after();
       {
         const uint64_t dK = umma_desc_k_sw128(smem_u32(sKV));
-        for (int q = 0; q < nq; ++q) {
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks) umma_f16_ss_warp(tS[q], dQ[q] + 2u * ks, dK + 2u * ks, idesc_s, ks ? 1u : 0u);
-          umma_commit_warp(&s_full[q]);
-        }
+        for (int ks = 0; ks < KSTEPS; ++ks) umma_f16_ss_warp(tS, dQ + 2u * ks, dK + 2u * ks, idesc_s, ks ? 1u : 0u);
+        umma_commit_warp(&s_full[q]);
       }
       int stage = 0;
       uint32_t phase = 0;
+      long long* trm = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) ? p.trace + 16 + 8 * q : nullptr;
       for (int j = 0; j < ntiles; ++j) {
+        if (trm && j < 32) trm[32 * j + 0] = clock64();
         int nstage = stage + 1;
         uint32_t nphase = phase;
         if (nstage == kTcStages) {
           nstage = 0;
           nphase ^= 1u;
         }
-        const bool more = j + 1 < ntiles;
-        if (more) {
+        if (j + 1 < ntiles) {                            // next scores: S_q is free once it sits in registers
           mbar_wait(&kv_full[nstage], nphase);
+          mbar_wait(&s_free[q], static_cast<uint32_t>(j & 1));
           tcgen05_fence_after();
+          const uint64_t dKn = umma_desc_k_sw128(smem_u32(sKV + nstage * 2 * kTcTileBytes));
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) umma_f16_ss_warp(tS, dQ + 2u * ks, dKn + 2u * ks, idesc_s, ks ? 1u : 0u);
+          umma_commit_warp(&s_full[q]);
+          if (trm && j < 32) trm[32 * j + 1] = clock64();            // QK(j+1) issued
         }
         const uint64_t dV = umma_desc_mn_sw128(smem_u32(sKV + stage * 2 * kTcTileBytes + kTcTileBytes), kTcTileBytes);
-        const uint64_t dKn = umma_desc_k_sw128(smem_u32(sKV + nstage * 2 * kTcTileBytes));
-        for (int q = 0; q < nq; ++q) {
-          mbar_wait(&p_full[q], static_cast<uint32_t>(j & 1));
-          tcgen05_fence_after();
+        mbar_wait(&p_full[q], static_cast<uint32_t>(j & 1));
+        tcgen05_fence_after();
+        if (trm && j < 32) trm[32 * j + 2] = clock64();              // P(j) seen
 #pragma unroll
-          for (int kk = 0; kk < kTcTile / 16; ++kk)     // 16 keys per step: P columns +8, V rows +16 (2 KiB)
-            umma_f16_ts_warp(tO[q], tP[q] + 8u * kk, dV + 128u * kk, idesc_o, (j | kk) ? 1u : 0u);
-          if (more) {
-#pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks) umma_f16_ss_warp(tS[q], dQ[q] + 2u * ks, dKn + 2u * ks, idesc_s, ks ? 1u : 0u);
-          }
-          umma_commit_warp(&s_full[q]);                      // S_q(j+1) ready / final: O_q complete
-        }
-        umma_commit_warp(&kv_empty[stage]);                  // K_j, V_j no longer needed
+        for (int kk = 0; kk < kTcTile / 16; ++kk)       // 16 keys per step: P columns +8, V rows +16 (2 KiB)
+          umma_f16_ts_warp(tO, ((kPx && kk < 2 && (j & 1)) ? tPx : tP) + 8u * kk, dV + 128u * kk, idesc_o, (j | kk) ? 1u : 0u);
+        umma_commit_warp(&o_done[q]);
+        umma_commit_warp(&kv_empty[stage]);                // this tile's K_j, V_j reads are done (count = nq)
+        if (trm && j < 32) trm[32 * j + 3] = clock64();              // P.V issued
         stage = nstage;
         phase = nphase;
       }
@@ -266,21 +316,36 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
     if (qt < nq) {
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
       const uint32_t tS = tmem_base + lane_off + (qt ? kTcColS1 : kTcColS0);
-      const uint32_t tO = tmem_base + lane_off + (qt ? kTcColO1 : kTcColO0);
+      const uint32_t tO = tmem_base + lane_off + (qt ? (kPx ? kTcColO1Small : kTcColO1) : kTcColO0);
       const uint32_t tP = tmem_base + lane_off + (qt ? kTcColP1 : kTcColP0);
+      const uint32_t tPx = tmem_base + lane_off + (qt ? kTcColX1 : kTcColX0);
       const float c = p.scale_log2;
       float mref = -INFINITY, l = 0.f;
+      // trace rows: tile j -> [32*j + 8*qt + k]: 0 tile start, 1 S ready, 2 S in registers, 3 max done, 4 P.V of the previous tile done, 5 P written, 6 p_full arrived; [32*j + 16 + ...]: MMA warp
+      long long* tr = (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && wq == 0 && lane == 0)
+                          ? p.trace + 8 * qt : nullptr;
+      // Stagger (p.stagger): left alone the two warpgroups run in lockstep - clock trace: their S load / row max / P.V
+      // wait phases coincide and the MUFU pipe idles a third of every tile.  Query tile 1 therefore starts its first
+      // key tile only after tile 0 is 1 = past its row maximum, 2 = half way through its exponentials.  (Strict
+      // alternation of the exponential phases was measured slower: one warp per sub-partition cannot saturate MUFU.)
+      const int stagger = nq == 2 ? p.stagger : 0;
+      if (stagger && qt == 1) named_bar_sync(1, 256);
       for (int j = 0; j < ntiles; ++j) {
+        if (tr && j < 32) tr[32 * j + 0] = clock64();
         const int seg = j < p.ntile[0] ? 0 : 1;
         const int valid = p.lkv[seg] - (seg == 0 ? j : j - p.ntile[0]) * kTcTile;   // keys of this tile that exist
         mbar_wait(&s_full[qt], static_cast<uint32_t>(j & 1));
         tcgen05_fence_after();
+        if (tr && j < 32) tr[32 * j + 1] = clock64();
         uint32_t r[128];
         tmem_ld_32x32b_x32(tS, r);
         tmem_ld_32x32b_x32(tS + 32, r + 32);
         tmem_ld_32x32b_x32(tS + 64, r + 64);
         tmem_ld_32x32b_x32(tS + 96, r + 96);
         tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&s_free[qt]);                            // the MMA warp may overwrite S_q with the next scores
+        if (tr && j < 32) tr[32 * j + 2] = clock64();
         if (valid < kTcTile) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -288,13 +353,14 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
         }
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          m0 = fmaxf(m0, __uint_as_float(r[i]));
-          m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
-          m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+        for (int i = 0; i < 128; i += 8) {
+          m0 = max3_f(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          m1 = max3_f(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          m2 = max3_f(m2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+          m3 = max3_f(m3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
         }
         const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
+        if (tr && j < 32) tr[32 * j + 3] = clock64();
         // lazy rescaling: keep the reference maximum unless the new one exceeds it by more than 2^8
         const bool need = mt > mref + 8.f;
         float alpha = 1.f;
@@ -302,7 +368,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
           alpha = ex2_approx(mref - mt);                 // 0 on the first tile (mref = -inf)
           mref = mt;
         }
+        bool owait = j > 0;                              // P_q / O_q still belong to P.V of the previous tile
         if (j > 0 && __any_sync(0xffffffffu, need)) {     // rare after the first tiles: 16 columns at a time
+          mbar_wait(&o_done[qt], static_cast<uint32_t>((j - 1) & 1));
+          tcgen05_fence_after();
+          owait = false;
 #pragma unroll 1
           for (int cc = 0; cc < NO; cc += 16) {
             uint32_t o[16];
@@ -313,6 +383,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
             tmem_st_x16(tO + cc, o);
           }
         }
+        if (stagger == 1 && qt == 0 && j == 0) named_bar_arrive(1, 256);
         l *= alpha;
         const float nm = -mref;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -321,10 +392,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[cc + i]), c, nm));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[cc + i + 1]), c, nm));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(r[cc + i + 2]), c, nm));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(r[cc + i + 3]), c, nm));
+            const float x0 = fmaf(__uint_as_float(r[cc + i]), c, nm), x1 = fmaf(__uint_as_float(r[cc + i + 1]), c, nm);
+            const float x2 = fmaf(__uint_as_float(r[cc + i + 2]), c, nm), x3 = fmaf(__uint_as_float(r[cc + i + 3]), c, nm);
+            const float p0 = ex2_approx(x0);
+            const float p1 = ex2_approx(x1);
+            const float p2 = EMU >= 2 ? ex2_poly(x2) : ex2_approx(x2);
+            const float p3 = EMU >= 1 ? ex2_poly(x3) : ex2_approx(x3);
             s0 += p0;
             s1 += p1;
             s2 += p2;
@@ -332,15 +405,23 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_cons
             pk[i >> 1] = pack_h2(p0, p1);
             pk[(i >> 1) + 1] = pack_h2(p2, p3);
           }
-          tmem_st_x16(tP + (cc >> 1), pk);               // P as packed fp16 pairs
+          if (cc == (kPx ? 32 : 0) && owait) {
+            mbar_wait(&o_done[qt], static_cast<uint32_t>((j - 1) & 1));
+            tcgen05_fence_after();
+          }
+          if (cc == (kPx ? 32 : 0) && tr && j < 32) tr[32 * j + 4] = clock64();
+          tmem_st_x16(((kPx && cc == 0 && (j & 1)) ? tPx : tP) + (cc >> 1), pk);   // P as packed fp16 pairs
+          if (cc == 32 && stagger == 2 && qt == 0 && j == 0) named_bar_arrive(1, 256);
         }
         l += (s0 + s1) + (s2 + s3);
         tmem_st_wait();
+        if (tr && j < 32) tr[32 * j + 5] = clock64();
         tcgen05_fence_before();
         mbar_arrive(&p_full[qt]);
+        if (tr && j < 32) tr[32 * j + 6] = clock64();
       }
       // ---- epilogue: O / l -> fp16 -> global ----
-      mbar_wait(&s_full[qt], static_cast<uint32_t>(ntiles & 1));
+      mbar_wait(&o_done[qt], static_cast<uint32_t>((ntiles - 1) & 1));
       tcgen05_fence_after();
       uint32_t o[NO];
 #pragma unroll
@@ -406,20 +487,20 @@ static bool make_kv_map(CUtensorMap* m, const void* base, int cols, int rows, lo
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int KSTEPS>
+template <int KSTEPS, int EMU>
 static int launch_tc(const CUtensorMap* maps, const FaTcParams& p, int frames, int heads, cudaStream_t st) {
   const int smem = 1024 + 2 * kTcTileBytes + kTcStages * 2 * kTcTileBytes + 256;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(flash_attn_tc_kernel<KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_err = cudaFuncSetAttribute(flash_attn_tc_kernel<KSTEPS, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   if (attr_err != cudaSuccess) {
     set_last_error("ccedit_attention(tc): cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     return CCEDIT_ERR_CUDA;
   }
   dim3 grid((p.lq + 2 * kTcTile - 1) / (2 * kTcTile), heads, frames);
-  flash_attn_tc_kernel<KSTEPS><<<grid, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  flash_attn_tc_kernel<KSTEPS, EMU><<<grid, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_attention(tc)");
   return CCEDIT_OK;
@@ -463,12 +544,30 @@ int attention_tc(const ccedit_attn_desc* a, cudaStream_t st) {
   p.lq = a->lq;
   p.d = a->d;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.trace = g_trace_buf;
+  static const int stagger = [] {                  // developer switch; default = the measured best
+    const char* e = getenv("CCEDIT_ATTN_STAGGER");
+    return e ? atoi(e) : kTcDefaultStagger;
+  }();
+  p.stagger = stagger;
   const int ks = (a->d + 15) / 16;
-  switch (ks) {
-    case 1: return launch_tc<1>(maps, p, a->frames, a->heads, st);
-    case 2: return launch_tc<2>(maps, p, a->frames, a->heads, st);
-    case 3: return launch_tc<3>(maps, p, a->frames, a->heads, st);
-    default: return launch_tc<4>(maps, p, a->frames, a->heads, st);
+  static const int emu = [] {                      // developer switch; default = the measured best
+    const char* e = getenv("CCEDIT_ATTN_EMU");
+    return e ? atoi(e) : kTcDefaultEmu;
+  }();
+  switch (ks * 4 + (emu < 0 ? 0 : emu > 2 ? 2 : emu)) {
+    case 4: return launch_tc<1, 0>(maps, p, a->frames, a->heads, st);
+    case 5: return launch_tc<1, 1>(maps, p, a->frames, a->heads, st);
+    case 6: return launch_tc<1, 2>(maps, p, a->frames, a->heads, st);
+    case 8: return launch_tc<2, 0>(maps, p, a->frames, a->heads, st);
+    case 9: return launch_tc<2, 1>(maps, p, a->frames, a->heads, st);
+    case 10: return launch_tc<2, 2>(maps, p, a->frames, a->heads, st);
+    case 12: return launch_tc<3, 0>(maps, p, a->frames, a->heads, st);
+    case 13: return launch_tc<3, 1>(maps, p, a->frames, a->heads, st);
+    case 14: return launch_tc<3, 2>(maps, p, a->frames, a->heads, st);
+    case 16: return launch_tc<4, 0>(maps, p, a->frames, a->heads, st);
+    case 17: return launch_tc<4, 1>(maps, p, a->frames, a->heads, st);
+    default: return launch_tc<4, 2>(maps, p, a->frames, a->heads, st);
   }
 }
 

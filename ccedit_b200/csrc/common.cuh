@@ -46,21 +46,23 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // SiLU with the fast-division intrinsic (MUFU.RCP + FMUL, ~2 ulp): the IEEE '/' drags a slow-path call into every use
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// exact-erf GELU (torch F.gelu default, reference attention.py:120-122).
-// erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the fp16 rounding of the result):
-//   erf(z) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z >= 0
-__device__ __forceinline__ float erf_as_f(float x) {
-  const float z = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = __expf(-z * z);
-  return copysignf(fmaf(-poly, e, 1.0f), x);
+// exact-erf GELU (torch F.gelu default, reference attention.py:120-122): gelu(x) = x * Phi(x).
+// Phi(-|x|) = exp2(q(-|x|)) with q a degree-6 minimax fit of log2(Phi) on [-5.5, 0] (Lawson iteration, tools/fit_gelu.py):
+// relative error of Phi <= 2.7e-5 INCLUDING the left tail (the erf form 0.5*(1+erf) cancels there), max |gelu error|
+// 4e-6; Phi(x > 0) = 1 - Phi(-x).  11 FMA-pipe instructions + one MUFU.EX2 per value - the erf form by Abramowitz &
+// Stegun 7.1.26 used before cost 17 + two MUFU and made the GEGLU epilogue (not the MMAs) pace the FF-in GEMM at K = 320.
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  const float a = fmaxf(-fabsf(x), -5.5f);
+  float q = fmaf(2.615377861722895e-05f, a, 6.609817238438444e-04f);
+  q = fmaf(q, a, 7.488313388526632e-03f);
+  q = fmaf(q, a, 5.197041696700614e-02f);
+  q = fmaf(q, a, -4.6032946090714766e-01f);
+  q = fmaf(q, a, 1.1505840052884075f);
+  q = fmaf(q, a, -1.00003606355367f);
+  float phi;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(phi) : "f"(q));
+  return x * (x > 0.f ? 1.0f - phi : phi);
 }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752440f)); }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier
@@ -134,6 +136,21 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       "%7}], [%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// TMA store (shared -> global, bulk async-group completion) and its group bookkeeping; issued by ONE thread, which is also
+// the thread that later waits for the group (bulk groups are per-thread).
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {   // at most N groups still READING their shared-memory source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
 // warp-collective TMA issue (see umma_*_warp below): whole converged warp calls, one elected lane issues

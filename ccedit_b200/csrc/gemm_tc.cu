@@ -59,6 +59,12 @@ struct GemmKParams {
   int flags;
   uint32_t idesc;
   long long* trace;   // diagnostics: per-tile phase clocks of CTA 0 (ccedit_gemm_trace), or nullptr
+  // staged (shared memory + TMA store) epilogue, see epilogue_staged
+  int wcols;          // output columns per epilogue warp (half of the tile's output columns)
+  int cb;             // columns per staging block (one TMA box): cb == wcols, or 64 with wcols == 128
+  int nbuf;           // tile buffers (1 or 2)
+  int tbuf_bytes;     // bytes of one tile buffer = 128 rows * 2 * wcols * 2
+  uint32_t swz_mask;  // TMA swizzle of a staging block as an XOR mask on the 16-byte chunk index (7 / 3 / 1 / 0)
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -295,21 +301,267 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Staged epilogue (small-K GEMMs, where the epilogue - not the MMAs - paces the tile; ccedit_gemm_trace: the direct
+// epilogue above spends ~940 clocks per 16-column chunk because thread = row makes every 16-byte global access of a
+// warp touch 32 different lines).  Here the only global traffic of the epilogue is TMA:
+//   * each epilogue warp owns 32 rows x W columns of the tile (warpgroup eg takes columns [eg*W, eg*W + W)) and a
+//     private region [32][W] fp16 of a tile buffer in shared memory (TMA-swizzled when a row is 32/64/128 bytes, so the
+//     row-per-thread 16-byte accesses are bank-conflict free);
+//   * res1 of tile i+1 is TMA-loaded into the region by the warp's own lane 0 while tile i is processed (two tile
+//     buffers; with one buffer - BN = 256 - right after the store of tile i has left shared memory);
+//   * the thread adds bias / time-embedding row / activation / residual to its TMEM row and overwrites the region in
+//     place; lane 0 stores the 32 x W box with one TMA store (rows past the end of the tensor are clipped by TMA).
+// ---------------------------------------------------------------------------------------------------------------
 template <int MODE, int NRES>
+__device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmRes,
+                                                uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                uint64_t* res_bar_all, float* sbias_all, uint8_t* tbuf, int warp,
+                                                int lane) {
+  constexpr bool GEGLU = MODE == kModeGeglu;
+  const int wq = warp & 3;            // TMEM lane quarter this warp may access
+  const int eg = (warp - 2) >> 2;     // column half of the tile
+  const int ew = warp - 2;            // 0..7
+  const int row = wq * 32 + lane;
+  const int W = p.wcols;
+  const int ncols_out = 2 * W;
+  const int nch = W >> 4;
+  const int nblk = W / p.cb;
+  const int blk_bytes = 32 * p.cb * 2;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.cb) * 2u;
+  float* sbias = sbias_all + ew * 256;
+  uint64_t* rbar = res_bar_all + ew * 2;
+  uint8_t* region0 = tbuf + ew * (32 * W * 2);
+
+  int l[4], qoff[4];
+  long long lo_r2 = 0;
+  {
+    int r = row, r0 = wq * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      l[i] = r % p.box[i];
+      r /= p.box[i];
+      qoff[i] = r0 % p.box[i];
+      r0 /= p.box[i];
+      if (NRES >= 2) lo_r2 += static_cast<long long>(l[i]) * p.r2[i];
+    }
+  }
+  int dig[5], inc[5], radix[5];
+  {
+    int t = blockIdx.x, g = gridDim.x;
+    radix[0] = p.n_tiles;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) radix[i + 1] = p.tiles[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      dig[i] = t % radix[i]; t /= radix[i];
+      inc[i] = g % radix[i]; g /= radix[i];
+    }
+  }
+  // residual of the first tile
+  if (NRES >= 1 && static_cast<int>(blockIdx.x) < p.total_tiles && lane == 0) {
+    mbar_arrive_expect_tx(&rbar[0], static_cast<uint32_t>(32 * W * 2));
+    for (int bk = 0; bk < nblk; ++bk)
+      tma_load_5d(region0 + bk * blk_bytes, tmRes, &rbar[0], dig[0] * ncols_out + eg * W + bk * p.cb,
+                  dig[1] * p.box[0] + qoff[0], dig[2] * p.box[1] + qoff[1], dig[3] * p.box[2] + qoff[2],
+                  dig[4] * p.box[3] + qoff[3]);
+  }
+  __syncwarp();
+
+  int as = 0, it = 0;
+  uint32_t aphase = 0, rph0 = 0, rph1 = 0;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    if (tracing && it < 64) p.trace[16 * it + 0] = clock64();
+    const int b = (p.nbuf == 2) ? (it & 1) : 0;
+    const int n_tile = dig[0];
+    bool valid = true;
+    long long off_r2 = lo_r2;
+    int rb_c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int base = dig[i + 1] * p.box[i];
+      valid = valid && (base + l[i] < p.odim[i]);
+      if (NRES >= 2) off_r2 += static_cast<long long>(base) * p.r2[i];
+      if (i == p.rb_dim) rb_c = min(base + l[i], p.odim[i] - 1);
+    }
+    const int col0_out = n_tile * ncols_out + eg * W;        // first output column of this warp
+    const __half* r2ptr = p.res2 + off_r2 + col0_out;        // dereferenced only if NRES >= 2 and valid
+    // next tile (mixed-radix add with carry)
+    int ndig[5];
+    {
+      int carry = 0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        int d = dig[i] + inc[i] + carry;
+        carry = d >= radix[i] ? 1 : 0;
+        ndig[i] = d - (carry ? radix[i] : 0);
+      }
+    }
+    const bool has_next = tile + static_cast<int>(gridDim.x) < p.total_tiles;
+
+    // ---- bias row of this warp's columns -> per-warp shared memory (GEGLU: W value columns, then W gate columns) ----
+    uint4 c2[2], n2[2];
+    if (NRES >= 2 && valid) ld_res(c2, r2ptr);
+    const float* rbptr = nullptr;
+    {
+      bool rb_uniform = false;
+      int rb_row = 0;
+      if (!GEGLU && p.rowbias) {
+        rb_row = p.rb_div == 1 ? rb_c : rb_c / p.rb_div;
+        rb_uniform = __all_sync(0xffffffffu, rb_row == __shfl_sync(0xffffffffu, rb_row, 0));
+        if (!rb_uniform && valid) rbptr = p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out;
+      }
+      const int nb = GEGLU ? 2 * W : W;
+      float bv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = lane + 32 * k;
+        const int src = n_tile * p.bn + (GEGLU ? (i < W ? eg * W + i : ncols_out + eg * W + (i - W)) : eg * W + i);
+        bv[k] = (p.bias && i < nb) ? __ldg(p.bias + src) : 0.f;
+        if (rb_uniform && i < nb) bv[k] += __ldg(p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out + i);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sbias[lane + 32 * k] = bv[k];
+    }
+    __syncwarp();
+    if (tracing && it < 64) p.trace[16 * it + 1] = clock64();
+
+    mbar_wait(&tfull_bar[as], aphase);
+    tcgen05_fence_after();
+    if (tracing && it < 64) p.trace[16 * it + 2] = clock64();
+    uint8_t* region = region0 + b * p.tbuf_bytes;
+    if (NRES >= 1) {
+      if (p.nbuf == 2 && has_next && lane == 0) {
+        bulk_wait_group_read<0>();                         // the store of tile it-1 has left the other buffer
+        uint8_t* other = region0 + (b ^ 1) * p.tbuf_bytes;
+        mbar_arrive_expect_tx(&rbar[b ^ 1], static_cast<uint32_t>(32 * W * 2));
+        for (int bk = 0; bk < nblk; ++bk)
+          tma_load_5d(other + bk * blk_bytes, tmRes, &rbar[b ^ 1], ndig[0] * ncols_out + eg * W + bk * p.cb,
+                      ndig[1] * p.box[0] + qoff[0], ndig[2] * p.box[1] + qoff[1], ndig[3] * p.box[2] + qoff[2],
+                      ndig[4] * p.box[3] + qoff[3]);
+      }
+      mbar_wait(&rbar[b], b ? rph1 : rph0);
+      if (b) rph1 ^= 1u; else rph0 ^= 1u;
+    } else {
+      if (lane == 0) {
+        if (p.nbuf == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();   // this buffer's last store has been read
+      }
+    }
+    __syncwarp();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * kAccStride) +
+                           static_cast<uint32_t>(eg * W);
+
+#pragma unroll 1
+    for (int ci = 0; ci < nch; ++ci) {
+      const int c = ci * 16;
+      uint32_t r[16];
+      float v[16];
+      tmem_ld_32x32b_x16(taddr + c, r);
+      // this thread's 32 bytes of the staging row: block (c / cb), 16-byte chunks k, k+1 (TMA swizzle = XOR on the chunk)
+      const int bk = c / p.cb;
+      const uint32_t inrow = static_cast<uint32_t>(c - bk * p.cb) * 2u;
+      const uint32_t o0 = static_cast<uint32_t>(lane) * row_bytes + inrow;
+      const uint32_t sw = ((o0 >> 7) & p.swz_mask) << 4;
+      uint8_t* blk = region + bk * blk_bytes;
+      uint4* s0 = reinterpret_cast<uint4*>(blk + (o0 ^ sw));
+      uint4* s1 = reinterpret_cast<uint4*>(blk + ((o0 + 16u) ^ sw));
+      uint4 c1[2];
+      if (NRES >= 1) { c1[0] = *s0; c1[1] = *s1; }
+      if (GEGLU) {
+        uint32_t g[16];
+        tmem_ld_32x32b_x16(taddr + ncols_out + c, g);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
+          const float4 bg = *reinterpret_cast<const float4*>(sbias + W + c + j);
+          v[j] = (__uint_as_float(r[j]) + bv.x) * gelu_erf_f(__uint_as_float(g[j]) + bg.x);
+          v[j + 1] = (__uint_as_float(r[j + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[j + 1]) + bg.y);
+          v[j + 2] = (__uint_as_float(r[j + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[j + 2]) + bg.z);
+          v[j + 3] = (__uint_as_float(r[j + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[j + 3]) + bg.w);
+        }
+      } else {
+        if (NRES >= 2 && valid && ci + 1 < nch) ld_res(n2, r2ptr + c + 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
+          v[j] = __uint_as_float(r[j]) + bv.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + bv.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+        }
+      }
+      if (rbptr) add_f32x16(v, rbptr + c);
+      if (MODE == kModeSilu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+      }
+      if (NRES >= 1) add_res(v, c1);
+      if (NRES >= 2 && valid) add_res(v, c2);
+      uint4 q0, q1;
+      q0.x = pack_half2(v[0], v[1]);
+      q0.y = pack_half2(v[2], v[3]);
+      q0.z = pack_half2(v[4], v[5]);
+      q0.w = pack_half2(v[6], v[7]);
+      q1.x = pack_half2(v[8], v[9]);
+      q1.y = pack_half2(v[10], v[11]);
+      q1.z = pack_half2(v[12], v[13]);
+      q1.w = pack_half2(v[14], v[15]);
+      *s0 = q0;
+      *s1 = q1;
+      if (NRES >= 2) { c2[0] = n2[0]; c2[1] = n2[1]; }
+    }
+    if (tracing && it < 64) p.trace[16 * it + 3] = clock64();
+    tcgen05_fence_before();
+    fence_proxy_async_smem();                                // this thread's staging writes -> visible to the TMA store
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&tempty_bar[as]);
+      for (int bk = 0; bk < nblk; ++bk)
+        tma_store_5d(tmOut, region + bk * blk_bytes, n_tile * ncols_out + eg * W + bk * p.cb, dig[1] * p.box[0] + qoff[0],
+                     dig[2] * p.box[1] + qoff[1], dig[3] * p.box[2] + qoff[2], dig[4] * p.box[3] + qoff[3]);
+      bulk_commit_group();
+      if (NRES >= 1 && p.nbuf == 1 && has_next) {
+        bulk_wait_group_read<0>();
+        mbar_arrive_expect_tx(&rbar[0], static_cast<uint32_t>(32 * W * 2));
+        for (int bk = 0; bk < nblk; ++bk)
+          tma_load_5d(region0 + bk * blk_bytes, tmRes, &rbar[0], ndig[0] * ncols_out + eg * W + bk * p.cb,
+                      ndig[1] * p.box[0] + qoff[0], ndig[2] * p.box[1] + qoff[1], ndig[3] * p.box[2] + qoff[2],
+                      ndig[4] * p.box[3] + qoff[3]);
+      }
+    }
+    __syncwarp();
+    if (tracing && it < 64) p.trace[16 * it + 4] = clock64();
+    as ^= 1;
+    if (as == 0) aphase ^= 1u;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dig[i] = ndig[i];
+  }
+  if (lane == 0) bulk_wait_group_read<0>();                  // shared memory must outlive the last store's read
+  __syncwarp();
+}
+
+template <int MODE, int NRES, bool STAGED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // SWIZZLE_128B wants 1024 B alignment
 
   const int stage_bytes = kABytes + p.bn * kBlockK * 2;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  // [stages x (A, B)] [STAGED: nbuf tile buffers] [barriers, 512 B] [per-warp bias rows]; every part a multiple of 1 KiB
+  uint8_t* tbuf = smem + p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tbuf + (STAGED ? p.nbuf * p.tbuf_bytes : 0));
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* sbias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [kEpiWarps][256] floats, 16 B aligned
+  uint64_t* res_bar = tempty_bar + 4;                                  // [kEpiWarps][2] (STAGED with a residual)
+  float* sbias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 512);  // [kEpiWarps][256] floats, 16 B aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -324,6 +576,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);
+    }
+    if (STAGED) {
+      tma_prefetch_desc(&tmOut);
+      if (NRES >= 1) tma_prefetch_desc(&tmRes);
+      for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&res_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -406,7 +663,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue warps =====================
-    epilogue_loop<MODE, NRES>(p, tmem_base, tfull_bar, tempty_bar, sbias_all, warp, lane);
+    if (STAGED)
+      epilogue_staged<MODE, NRES>(p, &tmOut, &tmRes, tmem_base, tfull_bar, tempty_bar, res_bar, sbias_all, tbuf, warp, lane);
+    else
+      epilogue_loop<MODE, NRES>(p, tmem_base, tfull_bar, tempty_bar, sbias_all, warp, lane);
   }
 
   tcgen05_fence_before();
@@ -448,17 +708,40 @@ int device_sm_count() {
 
 extern long long* g_trace_buf;
 
-template <int MODE, int NRES>
-static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
-                               int smem_bytes, cudaStream_t stream) {
+template <int MODE, int NRES, bool STAGED>
+static cudaError_t launch_gemm_t(const CUtensorMap* tm, const GemmKParams& p, int grid, int smem_bytes,
+                                 cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tap_gemm_kernel<MODE, NRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(tap_gemm_kernel<MODE, NRES, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024);
   });
   if (attr_err != cudaSuccess) return attr_err;
-  tap_gemm_kernel<MODE, NRES><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  tap_gemm_kernel<MODE, NRES, STAGED><<<grid, kGemmThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   return cudaGetLastError();
+}
+template <int MODE, int NRES>
+static cudaError_t launch_gemm(const CUtensorMap* tm, const GemmKParams& p, bool staged, int grid, int smem_bytes,
+                               cudaStream_t stream) {
+  return staged ? launch_gemm_t<MODE, NRES, true>(tm, p, grid, smem_bytes, stream)
+                : launch_gemm_t<MODE, NRES, false>(tm, p, grid, smem_bytes, stream);
+}
+
+// Output-side tensor map of the staged epilogue: the [d4][d3][d2][d1][cols] view behind `base` with box
+// (cb columns, the 32-row quarter of the tile box), TMA swizzle chosen by the row width of a staging block.
+static bool make_out_map(PFN_encodeTiled encode, CUtensorMap* m, const void* base, int cols, const int* odim,
+                         const long long* str, const int* sub, int cb) {
+  cuuint64_t dims[5] = {(cuuint64_t)cols, (cuuint64_t)odim[0], (cuuint64_t)odim[1], (cuuint64_t)odim[2], (cuuint64_t)odim[3]};
+  cuuint64_t strides[4] = {(cuuint64_t)str[0] * 2, (cuuint64_t)str[1] * 2, (cuuint64_t)str[2] * 2, (cuuint64_t)str[3] * 2};
+  cuuint32_t box[5] = {(cuuint32_t)cb, (cuuint32_t)sub[0], (cuuint32_t)sub[1], (cuuint32_t)sub[2], (cuuint32_t)sub[3]};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = cb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : cb == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
@@ -494,7 +777,9 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     return CCEDIT_ERR_CUDA;
   }
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tm[4];
+  CUtensorMap& tmA = tm[0];
+  CUtensorMap& tmB = tm[1];
   {
     cuuint64_t dims[5] = {(cuuint64_t)d->a_dims[0], (cuuint64_t)d->a_dims[1], (cuuint64_t)d->a_dims[2],
                           (cuuint64_t)d->a_dims[3], (cuuint64_t)d->a_dims[4]};
@@ -559,10 +844,69 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.idesc = umma_idesc_f16(kBlockM, d->bn);
   p.trace = g_trace_buf;
   const int stage_bytes = kABytes + d->bn * kBlockK * 2;
-  int stages = (192 * 1024) / stage_bytes;
+  const int kblocks = d->ntaps * p.kchunks;
+  const int nres = (d->res1 ? 1 : 0) + (d->res2 ? 1 : 0);
+  if (d->res2 && !d->res1) {
+    p.res1 = p.res2;
+    for (int i = 0; i < 4; ++i) p.r1[i] = p.r2[i];
+    p.res2 = nullptr;
+  }
+  const int fixed_bytes = 1024 /* alignment slack */ + 512 /* barriers */ + kEpiWarps * 256 * 4 /* bias rows */;
+  const int budget = 227 * 1024 - fixed_bytes;
+  // ---- staged (TMA) epilogue: for GEMMs whose K loop is too short to hide the row-per-thread global accesses ----
+  bool staged = false;
+  {
+    const int ncols_out = geglu ? d->bn / 2 : d->bn;
+    const char* force = getenv("CCEDIT_GEMM_EPI");       // developer switch: 0 = always direct, 1 = staged wherever legal
+    bool ok = ncols_out % 32 == 0 && (!force || atoi(force) != 0);
+    for (int i = 0; i < 4 && ok; ++i) {
+      ok = d->out_strides[i] % 8 == 0 && (!p.res1 || p.r1[i] % 8 == 0);
+      // a size-1 grid axis may carry any stride; TMA still wants it 16-byte aligned
+    }
+    ok = ok && (!p.res1 || (reinterpret_cast<uintptr_t>(p.res1) & 15) == 0);
+    const int W = ncols_out / 2;
+    const int cb = W == 128 ? 64 : W;
+    ok = ok && (cb <= 128) && (W % cb == 0);
+    if (ok) {
+      const int tbuf = kBlockM * ncols_out * 2;
+      // the K loop hides a direct epilogue of ~5-8k clocks once a tile has >= ~5k clocks of MMAs (measured: K = 1280, BN = 160 is faster direct)
+      const bool wanted = (force && atoi(force) != 0) || kblocks * d->bn <= 15 * 160;
+      int nbuf = nres >= 1 ? 2 : 1;
+      int st = (budget - nbuf * tbuf) / stage_bytes;
+      if (st < 3 && nbuf == 2) {
+        nbuf = 1;
+        st = (budget - tbuf) / stage_bytes;
+      }
+      if (wanted && st >= 3) {
+        staged = true;
+        p.wcols = W;
+        p.cb = cb;
+        p.nbuf = nbuf;
+        p.tbuf_bytes = tbuf;
+        p.swz_mask = cb == 64 ? 7u : cb == 32 ? 3u : cb == 16 ? 1u : 0u;
+        int sub[4], rem = 32;
+        for (int i = 0; i < 4; ++i) {
+          sub[i] = d->box[i] < rem ? d->box[i] : rem;
+          rem /= sub[i];
+        }
+        const int cols = geglu ? d->n / 2 : d->n;
+        if (!make_out_map(encode, &tm[2], d->out, cols, p.odim, p.ostr, sub, cb) ||
+            (p.res1 && !make_out_map(encode, &tm[3], p.res1, cols, p.odim, p.r1, sub, cb))) {
+          set_last_error("ccedit_gemm: cuTensorMapEncodeTiled(out/res) failed");
+          return CCEDIT_ERR_CUDA;
+        }
+        if (!p.res1) tm[3] = tm[2];
+      }
+    }
+  }
+  if (!staged) {
+    tm[2] = tm[0];
+    tm[3] = tm[0];
+  }
+  int stages = (staged ? budget - p.nbuf * p.tbuf_bytes : 192 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + 1024 + 512 + kEpiWarps * 256 * 4;
+  const int smem_bytes = stages * stage_bytes + (staged ? p.nbuf * p.tbuf_bytes : 0) + fixed_bytes;
 
   const int sms = device_sm_count();
   if (sms <= 0) {
@@ -570,20 +914,14 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     return CCEDIT_ERR_CUDA;
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  const int nres = (d->res1 ? 1 : 0) + (d->res2 ? 1 : 0);
-  if (d->res2 && !d->res1) {
-    p.res1 = p.res2;
-    for (int i = 0; i < 4; ++i) p.r1[i] = p.r2[i];
-    p.res2 = nullptr;
-  }
   cudaError_t err;
-  if (geglu) err = launch_gemm<kModeGeglu, 0>(tmA, tmB, p, grid, smem_bytes, stream);
+  if (geglu) err = launch_gemm<kModeGeglu, 0>(tm, p, staged, grid, smem_bytes, stream);
   else if (d->flags & CCEDIT_GEMM_SILU) {
     CCEDIT_CHECK_ARG(nres == 0, "ccedit_gemm: SiLU and residuals cannot be combined");
-    err = launch_gemm<kModeSilu, 0>(tmA, tmB, p, grid, smem_bytes, stream);
-  } else if (nres == 0) err = launch_gemm<kModePlain, 0>(tmA, tmB, p, grid, smem_bytes, stream);
-  else if (nres == 1) err = launch_gemm<kModePlain, 1>(tmA, tmB, p, grid, smem_bytes, stream);
-  else err = launch_gemm<kModePlain, 2>(tmA, tmB, p, grid, smem_bytes, stream);
+    err = launch_gemm<kModeSilu, 0>(tm, p, staged, grid, smem_bytes, stream);
+  } else if (nres == 0) err = launch_gemm<kModePlain, 0>(tm, p, staged, grid, smem_bytes, stream);
+  else if (nres == 1) err = launch_gemm<kModePlain, 1>(tm, p, staged, grid, smem_bytes, stream);
+  else err = launch_gemm<kModePlain, 2>(tm, p, staged, grid, smem_bytes, stream);
   if (err != cudaSuccess) {
     set_last_error("ccedit_gemm: launch failed: %s", cudaGetErrorString(err));
     return CCEDIT_ERR_CUDA;

@@ -329,7 +329,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         raise RuntimeError("ccedit_b200.layernorm: channel dimension must be contiguous")
     ldx = x2.stride(0)
     out = torch.empty(x.shape, dtype=torch.float16, device=x.device) if out is None else out
-    _call("layernorm", _lib.load().ccedit_layernorm,
+    _call("layernorm" + (f"[M={M},C={Cc}]" if _PROF_SHAPES else ""), _lib.load().ccedit_layernorm,
           (x2.data_ptr(), ldx, out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M, Cc, eps, _stream()), nbytes=2 * _nb(out))
     return out
 
@@ -373,7 +373,8 @@ def attention(q: torch.Tensor, segments: Sequence[KVSegment], heads: int, out: t
     a.scale = float(dh) ** -0.5 if scale is None else scale
     lkv = sum(seg.k.shape[1] for seg in segments)
     kvb = sum(2.0 * seg.k.shape[0] * seg.k.shape[1] * Cc * 2 for seg in segments)   # each K/V row read once (ideal)
-    _call("attention", _lib.load().ccedit_attention, (C.byref(a), _stream()), flops=4.0 * F * L * lkv * Cc,
+    _call("attention" + (f"[F={F},L={L},Lkv={lkv},d={dh}]" if _PROF_SHAPES else ""), _lib.load().ccedit_attention,
+          (C.byref(a), _stream()), flops=4.0 * F * L * lkv * Cc,
           nbytes=2.0 * F * L * Cc * 2 + kvb)
     return out
 
@@ -498,6 +499,33 @@ def to_half(src: torch.Tensor) -> torch.Tensor:
     _call("to_half", _lib.load().ccedit_to_half, (src.data_ptr(), dst.data_ptr(), src.numel(), _stream()),
           nbytes=_nb(src, dst))
     return dst
+
+
+def pack_hint_stem_weight(w: torch.Tensor, bias: torch.Tensor, device, cin_pad: int, kpad: int):
+    """Conv2d weight [16, Cin, 3, 3] -> fp16 [16][kpad] with k = tap*cin_pad + channel (tap = kh*3 + kw), fp32 bias."""
+    n, cin = w.shape[0], w.shape[1]
+    if n != 16 or cin > cin_pad or 9 * cin_pad > kpad:
+        raise RuntimeError(f"ccedit_b200.pack_hint_stem_weight: unsupported conv shape {tuple(w.shape)}")
+    wp = torch.zeros(n, 9, cin_pad, dtype=torch.float32)
+    wp[:, :, :cin] = w.detach().float().cpu().reshape(n, cin, 9).permute(0, 2, 1)
+    out = torch.zeros(n, kpad, dtype=torch.float32)
+    out[:, :9 * cin_pad] = wp.reshape(n, 9 * cin_pad)
+    return (out.to(device=device, dtype=torch.float16).contiguous(),
+            bias.detach().to(device=device, dtype=torch.float32).contiguous())
+
+
+def hint_stem01(x: torch.Tensor, w0: torch.Tensor, b0: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor) -> torch.Tensor:
+    """x: [F, H, W, 8] fp16 -> SiLU(conv3x3(SiLU(conv3x3(x)))) [F, H, W, 16]: the two full-resolution layers of the
+    ControlNet hint stem in one pass (weights from ``pack_hint_stem_weight`` with (cin_pad, kpad) = (8, 80), (16, 144))."""
+    _require(x, name="x")
+    if not x.is_contiguous() or x.shape[-1] != 8:
+        raise RuntimeError("ccedit_b200.hint_stem01: x must be contiguous [F, H, W, 8]")
+    F, H, W, _ = x.shape
+    y = torch.empty(F, H, W, 16, dtype=torch.float16, device=x.device)
+    _call("hint_stem01", _lib.load().ccedit_hint_stem01,
+          (x.data_ptr(), y.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), F, H, W, _stream()),
+          flops=2.0 * F * H * W * 16 * 9 * (3 + 16), nbytes=_nb(x, y))
+    return y
 
 
 # ---------------------------------------------------------------------------------------------------------------------

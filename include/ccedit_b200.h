@@ -160,6 +160,15 @@ int ccedit_add_center_frame(void* x, const void* y, int32_t B, int32_t T, int32_
 /* dst fp16 [n] = (half) src fp32 [n]  (the cast of c["crossattn"] to the model dtype, wrappers.py:164-166). */
 int ccedit_to_half(const float* src, void* dst, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * ControlNet hint stem, first two layers fused (controlmodel.py:215-219: conv3x3(hint_channels->16) + SiLU +
+ * conv3x3(16->16) + SiLU at the full hint resolution).  x: [F][H][W][8] fp16 (hint channels zero-padded to 8, as written by
+ * ccedit_ncthw_to_cl), y: [F][H][W][16] fp16.  w0: fp16 [16][80], k = tap*8 + channel (tap = kh*3+kw), zero padded;
+ * w1: fp16 [16][144], k = tap*16 + channel; b0, b1: fp32 [16].
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ccedit_hint_stem01(const void* x, void* y, const void* w0, const float* b0, const void* w1, const float* b1,
+                       int32_t F, int32_t H, int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,49 @@ def test_linear(ops, M, K, N, geglu, res):
     close(out, ref, f"linear {M}x{K}x{N}")
 
 
+@pytest.mark.parametrize("M,K,N,nres,geglu", [(40000, 320, 320, 1, False), (40000, 320, 320, 0, False),
+                                               (30000, 320, 1280, 1, False), (20000, 640, 640, 2, False),
+                                               (33000, 320, 2560, 0, True), (1000, 1280, 320, 1, False),
+                                               (20011, 320, 960, 0, False), (5000, 64, 64, 1, False),
+                                               (5000, 64, 32, 1, False)])
+def test_linear_staged_epilogue(ops, M, K, N, nres, geglu):
+    """Small-K GEMMs take the shared-memory + TMA-store epilogue (gemm_tc.cu: epilogue_staged): several tiles per CTA
+    (both tile buffers, both barrier phases), ragged last tile, strided output / residual views of wider buffers."""
+    a, w = rnd(M, K, seed=21), rnd(N, K, seed=22, scale=1 / math.sqrt(K))
+    b = rnd(N, seed=23).float()
+    pw = ops.pack_weight(w.float(), b, "cuda", geglu=geglu)
+    no = pw.n_out
+    wide = torch.full((M, no + 64), 7.0, dtype=torch.float16, device="cuda")
+    out = wide[:, 32:32 + no]
+    r1w = rnd(M, no + 16, seed=24).cuda()
+    r1 = r1w[:, 8:8 + no] if nres >= 1 else None
+    r2 = rnd(M, no, seed=25).cuda() if nres >= 2 else None
+    ops.gemm(a.cuda(), pw, out, res1=r1, res2=r2)
+    ref = F.linear(a.float(), w.float(), b)
+    if geglu:
+        v, g = ref.chunk(2, dim=-1)
+        ref = v * F.gelu(g)
+    if r1 is not None:
+        ref = ref + r1.float().cpu()
+    if r2 is not None:
+        ref = ref + r2.float().cpu()
+    close(out, ref, f"staged linear {M}x{K}x{N} nres={nres}")
+    assert bool((wide[:, :32] == 7).all()) and bool((wide[:, 32 + no:] == 7).all()), "wrote outside the output view"
+
+
+def test_linear_staged_epilogue_rowbias_per_row_group(ops):
+    """Time-embedding style row bias whose row changes inside a warp's 32 rows (non-uniform path) and per tile."""
+    M, K, N, div = 3000, 320, 320, 20
+    a, w = rnd(M, K, seed=31), rnd(N, K, seed=32, scale=1 / math.sqrt(K))
+    b = rnd(N, seed=33).float()
+    rb = rnd((M + div - 1) // div, N, seed=34).float()
+    pw = ops.pack_weight(w.float(), b, "cuda")
+    out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    ops.gemm(a.cuda(), pw, out, rowbias=rb.cuda(), rb_dim=0, rb_div=div, silu=True)
+    ref = F.silu(F.linear(a.float(), w.float(), b) + rb.repeat_interleave(div, 0)[:M])
+    close(out, ref, "staged linear + rowbias + SiLU")
+
+
 @pytest.mark.parametrize("Fr,H,W,Cin,Cout,emb,silu", [(2, 16, 24, 64, 64, False, False), (4, 8, 12, 320, 320, True, False),
                                                       (2, 32, 48, 8, 320, False, False), (2, 64, 96, 320, 4, False, False),
                                                       (2, 32, 32, 16, 32, False, True), (3, 16, 24, 960, 640, False, False),
@@ -72,6 +115,22 @@ def test_conv3x3(ops, Fr, H, W, Cin, Cout, emb, silu):
     if silu:
         ref = F.silu(ref)
     close(out[..., :Cout].permute(0, 3, 1, 2), ref, f"conv3x3 {Cin}->{Cout}")
+
+
+@pytest.mark.parametrize("Fr,H,W", [(2, 32, 128), (1, 40, 70), (3, 16, 64), (1, 5, 9)])
+def test_hint_stem_first_two_layers_fused(ops, Fr, H, W):
+    """controlmodel.py:215-219: conv3x3(3->16)+SiLU+conv3x3(16->16)+SiLU in one kernel (csrc/hint_stem.cu), ragged tiles."""
+    x = rnd(Fr, 3, H, W, seed=60)
+    w0, b0 = rnd(16, 3, 3, 3, seed=61, scale=1 / math.sqrt(27)), rnd(16, seed=62).float()
+    w1, b1 = rnd(16, 16, 3, 3, seed=63, scale=1 / math.sqrt(144)), rnd(16, seed=64).float()
+    x_cl = torch.zeros(Fr, H, W, 8, dtype=torch.float16)
+    x_cl[..., :3] = x.permute(0, 2, 3, 1)
+    p0 = ops.pack_hint_stem_weight(w0.float(), b0, "cuda", 8, 80)
+    p1 = ops.pack_hint_stem_weight(w1.float(), b1, "cuda", 16, 144)
+    out = ops.hint_stem01(x_cl.cuda(), *p0, *p1)
+    mid = F.silu(F.conv2d(x.float(), w0.float(), b0, padding=1)).half().float()   # the kernel keeps layer 0 in fp16
+    ref = F.silu(F.conv2d(mid, w1.float(), b1, padding=1))
+    close(out.permute(0, 3, 1, 2), ref, f"hint stem layers 0+1 {Fr}x{H}x{W}")
 
 
 def test_conv3x3_time_embedding_rows_with_padded_tiles(ops):

@@ -53,12 +53,19 @@ def trace():
     _lib.load().ccedit_gemm_trace(buf.data_ptr())
     bench(34, 6144, 8, 40, iters=1)
     _lib.load().ccedit_gemm_trace(None)
-    t = buf.cpu()
+    t = buf.cpu().view(32, 32)
     t0 = int(t[0, 0])
-    print("tile: start s_ready ld_done math_done st_done barrier issued  (clocks since start; deltas)")
-    for i in range(2, 26):
-        r = [int(x) - t0 for x in t[i, :7]]
-        print(f"{i:3d}: {r[0]:7d} wait={r[1]-r[0]:5d} ld={r[2]-r[1]:5d} math={r[3]-r[2]:5d} st={r[4]-r[3]:5d} bar={r[5]-r[4]:5d} issue={r[6]-r[5]:5d} | tile={r[6]-r[0]:6d}")
+    print("per key tile (clocks): q-tile 0 | q-tile 1 : start, waitS, ld, max, wait PV + turn, exp, arrive ; MMA warp: loop start, QK0, QK1 issued, P0 seen, PV0 issued, P1 seen, PV1 issued")
+    for j in range(2, 20):
+        row = []
+        for qt in range(2):
+            r = [int(x) - t0 for x in t[j, 8 * qt:8 * qt + 7]]
+            row.append(f"{r[0]:7d} wS={r[1]-r[0]:5d} ld={r[2]-r[1]:4d} mx={r[3]-r[2]:4d} pv+turn={r[4]-r[3]:5d} exp={r[5]-r[4]:5d} ar={r[6]-r[5]:4d} tile={r[6]-r[0]:5d}")
+        mm = []
+        for qt in range(2):
+            m = [int(x) - t0 for x in t[j, 16 + 8 * qt:16 + 8 * qt + 4]]
+            mm.append(f"mma{qt} {m[0]:7d} qk=+{m[1]-m[0]:5d} p=+{m[2]-m[0]:5d} pv=+{m[3]-m[0]:5d}")
+        print(f"{j:3d}: " + " | ".join(row) + " || " + " | ".join(mm))
 
 
 if __name__ == "__main__":

@@ -33,5 +33,5 @@ for name, fl, by, ms in recs:
     a[0] += 1; a[1] += fl; a[2] += by; a[3] += ms
 tot = sum(a[3] for a in agg.values())
 print(f"total {tot:.2f} ms over {len(recs)} launches")
-for name, (n, fl, by, ms) in sorted(agg.items(), key=lambda kv: -kv[1][3])[:70]:
+for name, (n, fl, by, ms) in sorted(agg.items(), key=lambda kv: -kv[1][3])[:120]:
     print(f"{ms:8.3f} ms {100 * ms / tot:5.1f}% n={n:3d} {ms / n * 1e3:8.1f} us/launch {fl / ms / 1e9 if fl else 0:7.1f} TF/s {by / ms / 1e6:7.0f} GB/s  {name}")
