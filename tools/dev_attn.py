@@ -77,5 +77,10 @@ if __name__ == "__main__":
                  (1, 6144, 6144, 8, 40), (2, 512, 512, 4, 64), (2, 200, 200, 4, 16), (1, 1, 1, 8, 40), (2, 640, 640, 8, 32)]:
         check(*args)
     check(2, 1024, 1024, 8, 40, scale=4.0)        # large logits: exercises the lazy rescaling
+    for args in [(2, 300, 300, 8, 80), (2, 200, 77, 8, 80), (2, 96, 96, 8, 160), (1, 384, 384, 8, 160), (2, 130, 70, 4, 96),
+                 (2, 500, 500, 2, 128), (1, 64, 200, 8, 24), (2, 1536, 1536, 8, 80)]:
+        check(*args)
     bench(34, 6144, 8, 40)
     bench(34, 1536, 8, 40)
+    bench(34, 1536, 8, 80)
+    bench(34, 384, 8, 160)
