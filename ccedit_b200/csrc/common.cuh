@@ -49,7 +49,7 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 // exact-erf GELU (torch F.gelu default, reference attention.py:120-122): gelu(x) = x * Phi(x).
 // Phi(-|x|) = exp2(q(-|x|)) with q a degree-6 minimax fit of log2(Phi) on [-5.5, 0] (Lawson iteration, tools/fit_gelu.py):
 // relative error of Phi <= 2.7e-5 INCLUDING the left tail (the erf form 0.5*(1+erf) cancels there), max |gelu error|
-// 4e-6; Phi(x > 0) = 1 - Phi(-x).  11 FMA-pipe instructions + one MUFU.EX2 per value - the erf form by Abramowitz &
+// 4e-6; Phi(x > 0) = 1 - Phi(-x).  9 FMA/ALU-pipe instructions + one MUFU.EX2 per value - the erf form by Abramowitz &
 // Stegun 7.1.26 used before cost 17 + two MUFU and made the GEGLU epilogue (not the MMAs) pace the FF-in GEMM at K = 320.
 __device__ __forceinline__ float gelu_erf_f(float x) {
   const float a = fmaxf(-fabsf(x), -5.5f);
@@ -61,7 +61,7 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   q = fmaf(q, a, -1.00003606355367f);
   float phi;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(phi) : "f"(q));
-  return x * (x > 0.f ? 1.0f - phi : phi);
+  return fmaf(-fabsf(x), phi, fmaxf(x, 0.f));      // x > 0: x - x Phi(-x);  x < 0: x Phi(x) = -|x| Phi(-|x|)
 }
 
 // ---------------------------------------------------------------------------------------------

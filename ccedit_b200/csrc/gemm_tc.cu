@@ -65,6 +65,9 @@ struct GemmKParams {
   int nbuf;           // tile buffers (1 or 2)
   int tbuf_bytes;     // bytes of one tile buffer = 128 rows * 2 * wcols * 2
   uint32_t swz_mask;  // TMA swizzle of a staging block as an XOR mask on the 16-byte chunk index (7 / 3 / 1 / 0)
+  // LayerNorm folded into the epilogue (template flag LNF): out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]
+  const float2* rowstats;
+  const float* colsum;
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -116,6 +119,7 @@ __device__ __forceinline__ void add_f32x16(float (&v)[16], const float* p) {
 //     thread-constant and a tile-uniform part.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kModePlain = 0, kModeGeglu = 1, kModeSilu = 2;
+constexpr int kBiasFloats = 512;             // per epilogue warp: 256 bias values + 256 column sums (LNF)
 
 __device__ __forceinline__ void ld_res(uint4 (&dst)[2], const __half* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -132,14 +136,15 @@ __device__ __forceinline__ void add_res(float (&v)[16], const uint4 (&r)[2]) {
   }
 }
 
-template <int MODE, int NRES>
+template <int MODE, int NRES, bool LNF>
 __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, float* sbias_all, int warp, int lane) {
   constexpr bool GEGLU = MODE == kModeGeglu;
   const int wq = warp & 3;            // TMEM lane quarter this warp may access
   const int eg = (warp - 2) >> 2;     // epilogue group: takes the 16-column chunks with (chunk index & 1) == eg
   const int row = wq * 32 + lane;
-  float* sbias = sbias_all + (warp - 2) * 256;
+  float* sbias = sbias_all + (warp - 2) * kBiasFloats;
+  float* scs = sbias + 256;             // column sums of the LayerNorm-folded weight (LNF)
   const int ncols_out = GEGLU ? p.bn / 2 : p.bn;
   const int nchunks = ncols_out >> 4;
 
@@ -190,6 +195,13 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
       if (i == p.rb_dim) rb_c = min(base + l[i], p.odim[i] - 1);   // clamp: rows of the tile padding must not index past rowbias
     }
     const int col0_out = n_tile * ncols_out;
+    float rstd = 1.f, nmr = 0.f;                              // LNF: 1/std and -mean/std of this thread's row
+    if (LNF) {
+      const int m = min(dig[1] * p.box[0] + l[0], p.odim[0] - 1);
+      const float2 st = __ldg(p.rowstats + m);
+      rstd = st.y;
+      nmr = -st.x * st.y;
+    }
     __half* optr = p.out + off_o + col0_out;
     const __half* r1ptr = p.res1 + off_r1 + col0_out;   // dereferenced only if NRES >= 1 and valid
     const __half* r2ptr = p.res2 + off_r2 + col0_out;
@@ -216,6 +228,13 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) sbias[lane + 32 * k] = bv[k];
+      if (LNF) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = lane + 32 * k;
+          scs[i] = i < p.bn ? __ldg(p.colsum + n_tile * p.bn + i) : 0.f;
+        }
+      }
     }
     __syncwarp();
     if (tracing && titer < 64) p.trace[16 * titer + 1] = clock64();
@@ -237,12 +256,22 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
-          const float4 bg = *reinterpret_cast<const float4*>(sbias + ncols_out + c + j);
-          v[j] = (__uint_as_float(r[j]) + bv.x) * gelu_erf_f(__uint_as_float(g[j]) + bg.x);
-          v[j + 1] = (__uint_as_float(r[j + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[j + 1]) + bg.y);
-          v[j + 2] = (__uint_as_float(r[j + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[j + 2]) + bg.z);
-          v[j + 3] = (__uint_as_float(r[j + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[j + 3]) + bg.w);
+          float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
+          float4 bg = *reinterpret_cast<const float4*>(sbias + ncols_out + c + j);
+          float a[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+          float e[4] = {__uint_as_float(g[j]), __uint_as_float(g[j + 1]), __uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])};
+          if (LNF) {
+            const float4 cv = *reinterpret_cast<const float4*>(scs + c + j);
+            const float4 cg = *reinterpret_cast<const float4*>(scs + ncols_out + c + j);
+            bv = make_float4(fmaf(nmr, cv.x, bv.x), fmaf(nmr, cv.y, bv.y), fmaf(nmr, cv.z, bv.z), fmaf(nmr, cv.w, bv.w));
+            bg = make_float4(fmaf(nmr, cg.x, bg.x), fmaf(nmr, cg.y, bg.y), fmaf(nmr, cg.z, bg.z), fmaf(nmr, cg.w, bg.w));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] *= rstd; e[q] *= rstd; }
+          }
+          v[j] = (a[0] + bv.x) * gelu_erf_f(e[0] + bg.x);
+          v[j + 1] = (a[1] + bv.y) * gelu_erf_f(e[1] + bg.y);
+          v[j + 2] = (a[2] + bv.z) * gelu_erf_f(e[2] + bg.z);
+          v[j + 3] = (a[3] + bv.w) * gelu_erf_f(e[3] + bg.w);
         }
       } else {
         // request the residual rows of this thread's next chunk while this one is processed
@@ -251,11 +280,15 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
-          v[j] = __uint_as_float(r[j]) + bv.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + bv.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+          float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
+          if (LNF) {
+            const float4 cv = *reinterpret_cast<const float4*>(scs + c + j);
+            bv = make_float4(fmaf(nmr, cv.x, bv.x), fmaf(nmr, cv.y, bv.y), fmaf(nmr, cv.z, bv.z), fmaf(nmr, cv.w, bv.w));
+          }
+          v[j] = fmaf(__uint_as_float(r[j]), rstd, bv.x);          // rstd == 1 unless LNF
+          v[j + 1] = fmaf(__uint_as_float(r[j + 1]), rstd, bv.y);
+          v[j + 2] = fmaf(__uint_as_float(r[j + 2]), rstd, bv.z);
+          v[j + 3] = fmaf(__uint_as_float(r[j + 3]), rstd, bv.w);
         }
       }
       if (valid) {
@@ -313,7 +346,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
 //   * the thread adds bias / time-embedding row / activation / residual to its TMEM row and overwrites the region in
 //     place; lane 0 stores the 32 x W box with one TMA store (rows past the end of the tensor are clipped by TMA).
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE, int NRES>
+template <int MODE, int NRES, bool LNF>
 __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmRes,
                                                 uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                                 uint64_t* res_bar_all, float* sbias_all, uint8_t* tbuf, int warp,
@@ -329,7 +362,8 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
   const int nblk = W / p.cb;
   const int blk_bytes = 32 * p.cb * 2;
   const uint32_t row_bytes = static_cast<uint32_t>(p.cb) * 2u;
-  float* sbias = sbias_all + ew * 256;
+  float* sbias = sbias_all + ew * kBiasFloats;
+  float* scs = sbias + 256;             // column sums of the LayerNorm-folded weight (LNF)
   uint64_t* rbar = res_bar_all + ew * 2;
   uint8_t* region0 = tbuf + ew * (32 * W * 2);
 
@@ -386,6 +420,13 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
       if (i == p.rb_dim) rb_c = min(base + l[i], p.odim[i] - 1);
     }
     const int col0_out = n_tile * ncols_out + eg * W;        // first output column of this warp
+    float rstd = 1.f, nmr = 0.f;                              // LNF: 1/std and -mean/std of this thread's row
+    if (LNF) {
+      const int m = min(dig[1] * p.box[0] + l[0], p.odim[0] - 1);
+      const float2 st = __ldg(p.rowstats + m);
+      rstd = st.y;
+      nmr = -st.x * st.y;
+    }
     const __half* r2ptr = p.res2 + off_r2 + col0_out;        // dereferenced only if NRES >= 2 and valid
     // next tile (mixed-radix add with carry)
     int ndig[5];
@@ -423,6 +464,14 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) sbias[lane + 32 * k] = bv[k];
+      if (LNF) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i = lane + 32 * k;
+          const int src = n_tile * p.bn + (GEGLU ? (i < W ? eg * W + i : ncols_out + eg * W + (i - W)) : eg * W + i);
+          scs[i] = i < nb ? __ldg(p.colsum + src) : 0.f;
+        }
+      }
     }
     __syncwarp();
     if (tracing && it < 64) p.trace[16 * it + 1] = clock64();
@@ -474,23 +523,37 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
-          const float4 bg = *reinterpret_cast<const float4*>(sbias + W + c + j);
-          v[j] = (__uint_as_float(r[j]) + bv.x) * gelu_erf_f(__uint_as_float(g[j]) + bg.x);
-          v[j + 1] = (__uint_as_float(r[j + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[j + 1]) + bg.y);
-          v[j + 2] = (__uint_as_float(r[j + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[j + 2]) + bg.z);
-          v[j + 3] = (__uint_as_float(r[j + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[j + 3]) + bg.w);
+          float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
+          float4 bg = *reinterpret_cast<const float4*>(sbias + W + c + j);
+          float a[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+          float e[4] = {__uint_as_float(g[j]), __uint_as_float(g[j + 1]), __uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])};
+          if (LNF) {
+            const float4 cv = *reinterpret_cast<const float4*>(scs + c + j);
+            const float4 cg = *reinterpret_cast<const float4*>(scs + W + c + j);
+            bv = make_float4(fmaf(nmr, cv.x, bv.x), fmaf(nmr, cv.y, bv.y), fmaf(nmr, cv.z, bv.z), fmaf(nmr, cv.w, bv.w));
+            bg = make_float4(fmaf(nmr, cg.x, bg.x), fmaf(nmr, cg.y, bg.y), fmaf(nmr, cg.z, bg.z), fmaf(nmr, cg.w, bg.w));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a[q] *= rstd; e[q] *= rstd; }
+          }
+          v[j] = (a[0] + bv.x) * gelu_erf_f(e[0] + bg.x);
+          v[j + 1] = (a[1] + bv.y) * gelu_erf_f(e[1] + bg.y);
+          v[j + 2] = (a[2] + bv.z) * gelu_erf_f(e[2] + bg.z);
+          v[j + 3] = (a[3] + bv.w) * gelu_erf_f(e[3] + bg.w);
         }
       } else {
         if (NRES >= 2 && valid && ci + 1 < nch) ld_res(n2, r2ptr + c + 16);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
-          v[j] = __uint_as_float(r[j]) + bv.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + bv.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+          float4 bv = *reinterpret_cast<const float4*>(sbias + c + j);
+          if (LNF) {
+            const float4 cv = *reinterpret_cast<const float4*>(scs + c + j);
+            bv = make_float4(fmaf(nmr, cv.x, bv.x), fmaf(nmr, cv.y, bv.y), fmaf(nmr, cv.z, bv.z), fmaf(nmr, cv.w, bv.w));
+          }
+          v[j] = fmaf(__uint_as_float(r[j]), rstd, bv.x);          // rstd == 1 unless LNF
+          v[j + 1] = fmaf(__uint_as_float(r[j + 1]), rstd, bv.y);
+          v[j + 2] = fmaf(__uint_as_float(r[j + 2]), rstd, bv.z);
+          v[j + 3] = fmaf(__uint_as_float(r[j + 3]), rstd, bv.w);
         }
       }
       if (rbptr) add_f32x16(v, rbptr + c);
@@ -543,7 +606,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
   __syncwarp();
 }
 
-template <int MODE, int NRES, bool STAGED>
+template <int MODE, int NRES, bool STAGED, bool LNF>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -561,7 +624,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint64_t* res_bar = tempty_bar + 4;                                  // [kEpiWarps][2] (STAGED with a residual)
-  float* sbias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 512);  // [kEpiWarps][256] floats, 16 B aligned
+  float* sbias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 512);  // [kEpiWarps][kBiasFloats], 16 B aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -664,9 +727,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ===================== epilogue warps =====================
     if (STAGED)
-      epilogue_staged<MODE, NRES>(p, &tmOut, &tmRes, tmem_base, tfull_bar, tempty_bar, res_bar, sbias_all, tbuf, warp, lane);
+      epilogue_staged<MODE, NRES, LNF>(p, &tmOut, &tmRes, tmem_base, tfull_bar, tempty_bar, res_bar, sbias_all, tbuf, warp, lane);
     else
-      epilogue_loop<MODE, NRES>(p, tmem_base, tfull_bar, tempty_bar, sbias_all, warp, lane);
+      epilogue_loop<MODE, NRES, LNF>(p, tmem_base, tfull_bar, tempty_bar, sbias_all, warp, lane);
   }
 
   tcgen05_fence_before();
@@ -708,24 +771,24 @@ int device_sm_count() {
 
 extern long long* g_trace_buf;
 
-template <int MODE, int NRES, bool STAGED>
+template <int MODE, int NRES, bool STAGED, bool LNF>
 static cudaError_t launch_gemm_t(const CUtensorMap* tm, const GemmKParams& p, int grid, int smem_bytes,
                                  cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tap_gemm_kernel<MODE, NRES, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(tap_gemm_kernel<MODE, NRES, STAGED, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024);
   });
   if (attr_err != cudaSuccess) return attr_err;
-  tap_gemm_kernel<MODE, NRES, STAGED><<<grid, kGemmThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+  tap_gemm_kernel<MODE, NRES, STAGED, LNF><<<grid, kGemmThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   return cudaGetLastError();
 }
-template <int MODE, int NRES>
+template <int MODE, int NRES, bool LNF = false>
 static cudaError_t launch_gemm(const CUtensorMap* tm, const GemmKParams& p, bool staged, int grid, int smem_bytes,
                                cudaStream_t stream) {
-  return staged ? launch_gemm_t<MODE, NRES, true>(tm, p, grid, smem_bytes, stream)
-                : launch_gemm_t<MODE, NRES, false>(tm, p, grid, smem_bytes, stream);
+  return staged ? launch_gemm_t<MODE, NRES, true, LNF>(tm, p, grid, smem_bytes, stream)
+                : launch_gemm_t<MODE, NRES, false, LNF>(tm, p, grid, smem_bytes, stream);
 }
 
 // Output-side tensor map of the staged epilogue: the [d4][d3][d2][d1][cols] view behind `base` with box
@@ -851,7 +914,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     for (int i = 0; i < 4; ++i) p.r1[i] = p.r2[i];
     p.res2 = nullptr;
   }
-  const int fixed_bytes = 1024 /* alignment slack */ + 512 /* barriers */ + kEpiWarps * 256 * 4 /* bias rows */;
+  const int fixed_bytes = 1024 /* alignment slack */ + 512 /* barriers */ + kEpiWarps * kBiasFloats * 4 /* bias rows */;
   const int budget = 227 * 1024 - fixed_bytes;
   // ---- staged (TMA) epilogue: for GEMMs whose K loop is too short to hide the row-per-thread global accesses ----
   bool staged = false;
@@ -903,7 +966,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     tm[2] = tm[0];
     tm[3] = tm[0];
   }
-  int stages = (staged ? budget - p.nbuf * p.tbuf_bytes : 192 * 1024) / stage_bytes;
+  int stages = (staged ? budget - p.nbuf * p.tbuf_bytes : (192 * 1024 < budget ? 192 * 1024 : budget)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + (staged ? p.nbuf * p.tbuf_bytes : 0) + fixed_bytes;
@@ -915,7 +978,19 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   cudaError_t err;
-  if (geglu) err = launch_gemm<kModeGeglu, 0>(tm, p, staged, grid, smem_bytes, stream);
+  const bool lnf = d->rowstats != nullptr;
+  CCEDIT_CHECK_ARG((d->rowstats != nullptr) == (d->colsum != nullptr), "ccedit_gemm: rowstats and colsum go together");
+  if (lnf) {
+    CCEDIT_CHECK_ARG(nres == 0 && !d->rowbias && !(d->flags & CCEDIT_GEMM_SILU),
+                     "ccedit_gemm: the LayerNorm fold cannot be combined with residuals / rowbias / SiLU");
+    CCEDIT_CHECK_ARG(d->out_dims[1] == 1 && d->out_dims[2] == 1 && d->out_dims[3] == 1,
+                     "ccedit_gemm: the LayerNorm fold needs a 2-D [M, C] problem (out_dims[1..3] == 1)");
+    CCEDIT_CHECK_ARG((reinterpret_cast<uintptr_t>(d->rowstats) & 7) == 0, "ccedit_gemm: rowstats must be 8-byte aligned");
+    p.rowstats = reinterpret_cast<const float2*>(d->rowstats);
+    p.colsum = d->colsum;
+    err = geglu ? launch_gemm<kModeGeglu, 0, true>(tm, p, staged, grid, smem_bytes, stream)
+                : launch_gemm<kModePlain, 0, true>(tm, p, staged, grid, smem_bytes, stream);
+  } else if (geglu) err = launch_gemm<kModeGeglu, 0>(tm, p, staged, grid, smem_bytes, stream);
   else if (d->flags & CCEDIT_GEMM_SILU) {
     CCEDIT_CHECK_ARG(nres == 0, "ccedit_gemm: SiLU and residuals cannot be combined");
     err = launch_gemm<kModeSilu, 0>(tm, p, staged, grid, smem_bytes, stream);

@@ -289,7 +289,7 @@ __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restr
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        long long M, int C, float eps) {
+                                                        long long M, int C, float eps, float2* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
   if (row0 >= M) return;
@@ -331,6 +331,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     rstd[r] = rsqrtf(q / static_cast<float>(C) + eps);
+  }
+  if (stats) {                                           // statistics only: the normalisation is folded into the next GEMM
+    if (lane == 0) {
+      stats[row0] = make_float2(mean[0], rstd[0]);
+      if (two) stats[row0 + 1] = make_float2(mean[1], rstd[1]);
+    }
+    return;
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -404,27 +411,131 @@ extern "C" int ccedit_groupnorm_temporal(const void* x, void* y, const float* ga
   return CCEDIT_OK;
 }
 
-extern "C" int ccedit_layernorm(const void* x, int64_t ldx, void* y, const float* gamma, const float* beta, int64_t M,
-                                int32_t C, float eps, void* stream) {
-  CCEDIT_CHECK_ARG(x && y && gamma && beta, "ccedit_layernorm: null pointer");
+// Row statistics only (LayerNorm folded into the consuming GEMM): one warp per FOUR rows, the rows stay packed in
+// registers (NV uint4 per lane and row) so that ~2.5 KB per warp are in flight; two-pass variance on the register copy.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_stats_kernel(const __half* __restrict__ x, long long ldx,
+                                                              float2* __restrict__ stats, long long M, int C, float eps) {
+  constexpr int R = 4;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= M) return;
+  const int nvec = C >> 3;
+  uint4 v[R][NV];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r < M ? row0 + r : M - 1;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int iv = lane + 32 * i;
+      v[r][i] = iv < nvec ? __ldg(xr + iv) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  const float invc = 1.f / static_cast<float>(C);
+  float mean[R], q[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack8(v[r][i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[j];
+    }
+    mean[r] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    mean[r] *= invc;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+        float f[8];
+        unpack8(v[r][i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dlt = f[j] - mean[r];
+          a = fmaf(dlt, dlt, a);
+        }
+      }
+    }
+    q[r] = a;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+  if (lane < R && row0 + lane < M) {
+    float m = mean[0], qq = q[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r)
+      if (lane == r) { m = mean[r]; qq = q[r]; }
+    stats[row0 + lane] = make_float2(m, rsqrtf(qq * invc + eps));
+  }
+}
+
+static int layernorm_launch(const char* what, const void* x, int64_t ldx, void* y, const float* gamma, const float* beta,
+                            int64_t M, int32_t C, float eps, float* stats, void* stream) {
+  using namespace ccedit;
   CCEDIT_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0 && C <= 2560 && ldx % 8 == 0,
-                   "ccedit_layernorm: bad shape M=%lld C=%d ldx=%lld (C %% 8 == 0, C <= 2560)", (long long)M, C, (long long)ldx);
+                   "%s: bad shape M=%lld C=%d ldx=%lld (C %% 8 == 0, C <= 2560)", what, (long long)M, C, (long long)ldx);
   const int wpb = 8;
   const long long grid = (M + 2 * wpb - 1) / (2 * wpb);
   const dim3 g(static_cast<unsigned>(grid));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __half* xp = static_cast<const __half*>(x);
   __half* yp = static_cast<__half*>(y);
+  float2* sp = reinterpret_cast<float2*>(stats);
   const int nv = (C / 8 + 31) / 32;
   switch (nv) {
-    case 1: layernorm_kernel<1><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
-    case 2: layernorm_kernel<2><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
-    case 3: layernorm_kernel<3><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
+    case 1: layernorm_kernel<1><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps, sp); break;
+    case 2: layernorm_kernel<2><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps, sp); break;
+    case 3: layernorm_kernel<3><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps, sp); break;
     case 4:
-    case 5: layernorm_kernel<5><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
-    default: layernorm_kernel<10><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps); break;
+    case 5: layernorm_kernel<5><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps, sp); break;
+    default: layernorm_kernel<10><<<g, wpb * 32, 0, st>>>(xp, ldx, yp, gamma, beta, M, C, eps, sp); break;
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_layernorm");
+  CCEDIT_CUDA_LAUNCH_CHECK(what);
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_layernorm(const void* x, int64_t ldx, void* y, const float* gamma, const float* beta, int64_t M,
+                                int32_t C, float eps, void* stream) {
+  CCEDIT_CHECK_ARG(x && y && gamma && beta, "ccedit_layernorm: null pointer");
+  return layernorm_launch("ccedit_layernorm", x, ldx, y, gamma, beta, M, C, eps, nullptr, stream);
+}
+
+extern "C" int ccedit_layernorm_stats(const void* x, int64_t ldx, float* stats, int64_t M, int32_t C, float eps,
+                                      void* stream) {
+  using namespace ccedit;
+  CCEDIT_CHECK_ARG(x && stats, "ccedit_layernorm_stats: null pointer");
+  CCEDIT_CHECK_ARG((reinterpret_cast<uintptr_t>(stats) & 7) == 0, "ccedit_layernorm_stats: stats must be 8-byte aligned");
+  CCEDIT_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0 && C <= 2560 && ldx % 8 == 0,
+                   "ccedit_layernorm_stats: bad shape M=%lld C=%d ldx=%lld (C %% 8 == 0, C <= 2560)", (long long)M, C,
+                   (long long)ldx);
+  const int nv = (C / 8 + 31) / 32;
+  if (nv > 5)                                            // very wide rows: the register-light generic kernel
+    return layernorm_launch("ccedit_layernorm_stats", x, ldx, nullptr, nullptr, nullptr, M, C, eps, stats, stream);
+  const int wpb = 8;
+  const dim3 g(static_cast<unsigned>((M + 4 * wpb - 1) / (4 * wpb)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __half* xp = static_cast<const __half*>(x);
+  float2* sp = reinterpret_cast<float2*>(stats);
+  switch (nv) {
+    case 1: layernorm_stats_kernel<1><<<g, wpb * 32, 0, st>>>(xp, ldx, sp, M, C, eps); break;
+    case 2: layernorm_stats_kernel<2><<<g, wpb * 32, 0, st>>>(xp, ldx, sp, M, C, eps); break;
+    case 3: layernorm_stats_kernel<3><<<g, wpb * 32, 0, st>>>(xp, ldx, sp, M, C, eps); break;
+    default: layernorm_stats_kernel<5><<<g, wpb * 32, 0, st>>>(xp, ldx, sp, M, C, eps); break;
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_layernorm_stats");
   return CCEDIT_OK;
 }

@@ -74,6 +74,17 @@ class ParamHolder(nn.Module):
             return ops.pack_weight(w, b, device, geglu=geglu, max_bn=max_bn)
         return self._cached((device, "w", geglu, scale, max_bn), make)
 
+    def packed_ln(self, device, ln: "ParamHolder", geglu=False) -> PackedWeight:
+        """This Linear with the LayerNorm ``ln`` that feeds it folded in (ops.pack_weight(ln_gamma=...)); rebuilt when
+        either parameter set changes."""
+        key = (device, "w_ln", geglu)
+        ver = (self._version(), ln._version())
+        c = self._cache.get(key)
+        if c is None or c[0] != ver:
+            self._cache[key] = c = (ver, ops.pack_weight(self.weight, self.bias, device, geglu=geglu,
+                                                         ln_gamma=ln.weight, ln_beta=ln.bias))
+        return c[1]
+
     def affine(self, device):
         return self._cached((device, "affine"), lambda: (
             self.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
@@ -104,10 +115,13 @@ def seq(**mods):
     return nn.ModuleDict({k.lstrip("_"): v for k, v in mods.items()})
 
 
-def _fused(device, holders: List[ParamHolder], geglu=False) -> PackedWeight:
-    """Pack the row-concatenation of several bias-free projections (QKV / KV) as one weight."""
+def _fused(device, holders: List[ParamHolder], geglu=False, ln: Optional[ParamHolder] = None) -> PackedWeight:
+    """Pack the row-concatenation of several bias-free projections (QKV / KV) as one weight (optionally with the
+    LayerNorm that feeds all of them folded in)."""
     w = torch.cat([h.weight.detach().float() for h in holders], 0)
-    return ops.pack_weight(w, None, device, geglu=geglu)
+    if ln is None:
+        return ops.pack_weight(w, None, device, geglu=geglu)
+    return ops.pack_weight(w, None, device, geglu=geglu, ln_gamma=ln.weight, ln_beta=ln.bias)
 
 
 def _new(ref: torch.Tensor, *shape):
@@ -143,12 +157,13 @@ class CrossAttention(nn.Module):
         self.to_out = seq(_0=linear(inner, query_dim))
         self._pk = {}
 
-    def fused(self, device, which):
+    def fused(self, device, which, ln: Optional[ParamHolder] = None):
         hs = {"qkv": [self.to_q, self.to_k, self.to_v], "kv": [self.to_k, self.to_v]}[which]
-        ver = tuple(h._version() for h in hs)
-        c = self._pk.get((device, which))
+        ver = tuple(h._version() for h in hs) + ((ln._version(),) if ln is not None else ())
+        key = (device, which, ln is not None)
+        c = self._pk.get(key)
         if c is None or c[0] != ver:
-            self._pk[(device, which)] = c = (ver, _fused(device, hs))
+            self._pk[key] = c = (ver, _fused(device, hs, ln=ln))
         return c[1]
 
     def invalidate(self):
@@ -163,11 +178,13 @@ class FeedForward(nn.Module):
         inner = dim * mult
         self.net = seq(_0=nn.ModuleDict({"proj": linear(dim, inner * 2)}), _2=linear(inner, dim))
 
-    def run(self, xn, res, out=None):
-        dev = xn.device
-        g = ops.gemm(xn, self.net["0"]["proj"].packed(dev, geglu=True), _new(xn, xn.shape[0], self.net["2"].weight.shape[1]))
-        out = _new(xn, *res.shape) if out is None else out
-        return ops.gemm(g, self.net["2"].packed(dev), out, res1=res)
+    def run(self, x, ln: ParamHolder, stats, out=None):
+        """x + net.2(GEGLU(net.0(LN(x)))): the LayerNorm ``ln`` is folded into the GEGLU GEMM (``stats`` = row statistics)."""
+        dev = x.device
+        g = ops.gemm(x, self.net["0"]["proj"].packed_ln(dev, ln, geglu=True),
+                     _new(x, x.shape[0], self.net["2"].weight.shape[1]), rowstats=stats)
+        out = _new(x, *x.shape) if out is None else out
+        return ops.gemm(g, self.net["2"].packed(dev), out, res1=x)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -183,18 +200,19 @@ class BasicTransformerBlock(nn.Module):
     def run(self, x, F, L, ctx: Ctx):
         dev, C, M = x.device, x.shape[1], x.shape[0]
         heads = self.attn1.heads
-        n1 = ops.layernorm(x, *self.norm1.affine(dev))
-        qkv = ops.gemm(n1, self.attn1.fused(dev, "qkv"), _new(x, M, 3 * C))
+        # the three LayerNorms are folded into the GEMMs they feed: one statistics pass each (ops.layernorm_stats)
+        st = ops.layernorm_stats(x)
+        qkv = ops.gemm(x, self.attn1.fused(dev, "qkv", ln=self.norm1), _new(x, M, 3 * C), rowstats=st)
         q3 = qkv.view(F, L, 3 * C)
         att = ops.attention(q3[..., :C], [KVSegment(q3[..., C:2 * C], q3[..., 2 * C:])], heads, _new(x, F, L, C))
         x = ops.gemm(att.view(M, C), self.attn1.to_out["0"].packed(dev), _new(x, M, C), res1=x)
-        n2 = ops.layernorm(x, *self.norm2.affine(dev))
-        q = ops.gemm(n2, self.attn2.to_q.packed(dev), _new(x, M, C))
+        ops.layernorm_stats(x, out=st)
+        q = ops.gemm(x, self.attn2.to_q.packed_ln(dev, self.norm2), _new(x, M, C), rowstats=st)
         k, v = ctx.text_kv[id(self.attn2)]
         att = ops.attention(q.view(F, L, C), [KVSegment(k, v, div=ctx.T)], heads, att)
         x = ops.gemm(att.view(M, C), self.attn2.to_out["0"].packed(dev), _new(x, M, C), res1=x)
-        n3 = ops.layernorm(x, *self.norm3.affine(dev), out=n2)
-        return self.ff.run(n3, x)
+        ops.layernorm_stats(x, out=st)
+        return self.ff.run(x, self.norm3, st)
 
 
 class BasicTransformerSingleLayerBlock(nn.Module):
@@ -209,13 +227,13 @@ class BasicTransformerSingleLayerBlock(nn.Module):
     def run(self, x, attend, out=None):
         """x: tokens [M, C]; attend(q [M,C], kv [M,2C]) -> [M, C] runs the attention of the calling layer."""
         dev, C, M = x.device, x.shape[1], x.shape[0]
-        n1 = ops.layernorm(x, *self.norm1.affine(dev))
-        q = ops.gemm(n1, self.attn1.to_q.packed(dev), _new(x, M, C))
+        st = ops.layernorm_stats(x)
+        q = ops.gemm(x, self.attn1.to_q.packed_ln(dev, self.norm1), _new(x, M, C), rowstats=st)
         kv = ops.gemm(x, self.attn1.fused(dev, "kv"), _new(x, M, 2 * C))
         att = attend(q, kv)
         x = ops.gemm(att, self.attn1.to_out["0"].packed(dev), _new(x, M, C), res1=x)
-        n2 = ops.layernorm(x, *self.norm2.affine(dev), out=n1)
-        return self.ff.run(n2, x, out)
+        ops.layernorm_stats(x, out=st)
+        return self.ff.run(x, self.norm2, st, out)
 
 
 class SpatialTransformer(nn.Module):

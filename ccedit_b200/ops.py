@@ -95,6 +95,7 @@ class PackedWeight:
     ntaps: int
     bn: int
     geglu: bool = False
+    colsum: Optional[torch.Tensor] = None   # fp32 [n]: row sums of the fp16 weight, present when a LayerNorm is folded in
 
     @property
     def n_out(self) -> int:
@@ -102,16 +103,29 @@ class PackedWeight:
 
 
 def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor], device, geglu: bool = False, n_pad_to: int = 16,
-                cin_pad_to: int = 8, max_bn: int = 256) -> PackedWeight:
+                cin_pad_to: int = 8, max_bn: int = 256, ln_gamma: Optional[torch.Tensor] = None,
+                ln_beta: Optional[torch.Tensor] = None) -> PackedWeight:
     """w: [N, Cin, *taps] in the reference (PyTorch) layout: Linear [N,K], Conv2d [N,Cin,kh,kw], Conv1d [N,Cin,kt].
 
     Tap order is row-major over the kernel dims (kh*3+kw / kt), matching ``conv_taps``/``temporal_taps``.
+    ``ln_gamma``/``ln_beta`` fold the LayerNorm that feeds this Linear into it (attention.py:667-669 -> to_q/ff.net.0):
+    LN(x) W^T + b = rstd * (x (gamma o W)^T - mean * colsum(gamma o W)) + (b + W beta); ``gemm(..., rowstats=)`` applies
+    the per-row part, the packed weight carries gamma o W, its fp16 row sums and the shifted bias.
     GEGLU: rows are re-ordered so that every BN tile holds BN/2 value rows followed by their BN/2 gate rows
     (reference: value = first half of the 2*inner outputs, gate = second half; attention.py:120-122).
     """
     w = w.detach().to(torch.float32)
     n, cin = w.shape[0], w.shape[1]
     ntaps = int(math.prod(w.shape[2:])) if w.dim() > 2 else 1
+    fold = ln_gamma is not None
+    if fold:
+        if w.dim() != 2:
+            raise ValueError("LayerNorm folding applies to Linear weights only")
+        g32 = ln_gamma.detach().to(device=w.device, dtype=torch.float32)
+        b32 = ln_beta.detach().to(device=w.device, dtype=torch.float32)
+        shift = w @ b32
+        bias = shift if bias is None else bias.detach().to(device=w.device, dtype=torch.float32) + shift
+        w = w * g32[None, :]
     w = w.reshape(n, cin, ntaps).permute(0, 2, 1)  # [N, taps, Cin]
     b = None if bias is None else bias.detach().to(torch.float32)
     n_p = ((n + n_pad_to - 1) // n_pad_to) * n_pad_to
@@ -135,7 +149,8 @@ def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor], device, geglu: bo
     wp[:, :, :cin] = w
     wp = wp.reshape(n_p, ntaps * kpad).to(device=device, dtype=torch.float16).contiguous()
     bp = None if b is None else b.to(device=device, dtype=torch.float32).contiguous()
-    return PackedWeight(wp, bp, n_p, cin, kpad, ntaps, bn, geglu)
+    cs = wp.float().sum(1).contiguous() if fold else None     # sums of the ROUNDED weights: the mean term cancels exactly
+    return PackedWeight(wp, bp, n_p, cin, kpad, ntaps, bn, geglu, cs)
 
 
 def conv_taps():
@@ -203,7 +218,7 @@ def _dims_strides(t: torch.Tensor):
 def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = ONE_TAP, *,
          rowbias: Optional[torch.Tensor] = None, rb_dim: int = 0, rb_div: int = 1,
          res1: Optional[torch.Tensor] = None, res2: Optional[torch.Tensor] = None, silu: bool = False,
-         box: Optional[tuple] = None) -> torch.Tensor:
+         box: Optional[tuple] = None, rowstats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[p, :] = epi( sum_tap A[p + tap, :] @ W[:, tap, :]^T ).  a/out/res*: [d4, d3, d2, d1, C] views (C contiguous)."""
     _require(a, name="a")
     _require(out, name="out")
@@ -256,6 +271,14 @@ def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = 
         for i in range(4):
             arr[i] = rstr[i]
     d.flags = (_lib.GEMM_SILU if silu else 0) | (_lib.GEMM_GEGLU if pw.geglu else 0)
+    if (rowstats is not None) != (pw.colsum is not None):
+        raise RuntimeError("ccedit_b200.gemm: rowstats go with a LayerNorm-folded weight (pack_weight(ln_gamma=...)) and vice versa")
+    if rowstats is not None:
+        _require(rowstats, torch.float32, "rowstats")
+        if rowstats.shape != (odims[0], 2) or not rowstats.is_contiguous():
+            raise RuntimeError(f"ccedit_b200.gemm: rowstats must be contiguous [{odims[0]}, 2]")
+        d.rowstats = rowstats.data_ptr()
+        d.colsum = pw.colsum.data_ptr()
     m_rows = math.prod(odims)
     kind = {1: "gemm.linear", 3: "gemm.temporal_k3", 9: "gemm.conv3x3"}.get(len(taps), "gemm.other")
     if pw.geglu:
@@ -331,6 +354,21 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     out = torch.empty(x.shape, dtype=torch.float16, device=x.device) if out is None else out
     _call("layernorm" + (f"[M={M},C={Cc}]" if _PROF_SHAPES else ""), _lib.load().ccedit_layernorm,
           (x2.data_ptr(), ldx, out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M, Cc, eps, _stream()), nbytes=2 * _nb(out))
+    return out
+
+
+def layernorm_stats(x: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [M, C] (row stride free) -> fp32 [M, 2] = (mean, 1/sqrt(var + eps)) per row, for a LayerNorm folded into the
+    consuming GEMM (``pack_weight(ln_gamma=...)`` + ``gemm(rowstats=...)``): one read of x instead of read + write + read."""
+    _require(x, name="x")
+    Cc = x.shape[-1]
+    x2 = x.reshape(-1, Cc) if x.is_contiguous() else x
+    if x2.dim() != 2 or x2.stride(1) != 1:
+        raise RuntimeError("ccedit_b200.layernorm_stats: x must be [M, C] with contiguous channels")
+    M = x2.shape[0]
+    out = torch.empty(M, 2, dtype=torch.float32, device=x.device) if out is None else out
+    _call("layernorm_stats" + (f"[M={M},C={Cc}]" if _PROF_SHAPES else ""), _lib.load().ccedit_layernorm_stats,
+          (x2.data_ptr(), x2.stride(0), out.data_ptr(), M, Cc, eps, _stream()), nbytes=_nb(x2) + out.numel() * 4)
     return out
 
 

@@ -79,6 +79,13 @@ typedef struct ccedit_gemm_desc {
   const void* res2;       /* fp16 or NULL                                                           */
   int64_t res2_strides[4];
   int32_t flags;          /* CCEDIT_GEMM_*                                                          */
+  /* LayerNorm folded into this GEMM (attention.py:667-669 feeding to_q / to_k / to_v / ff.net.0): A holds the
+   * UN-normalised tokens, W is gamma o W, bias is bias + W beta, and the epilogue applies
+   *   out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]        (before GEGLU / SiLU)
+   * rowstats: fp32 (mean, rstd) pairs from ccedit_layernorm_stats, indexed by the d1 coordinate (out_dims[1..3] must be 1);
+   * colsum: fp32 [n] = sum_k fp16(W[n][k]).  Both NULL => no fold.  Not combinable with rowbias / residuals. */
+  const float* rowstats;
+  const float* colsum;
 } ccedit_gemm_desc;
 
 int ccedit_gemm(const ccedit_gemm_desc* d, void* stream);
@@ -103,6 +110,9 @@ int ccedit_groupnorm_temporal(const void* x, void* y, const float* gamma, const 
 /* x: [M][C] with row stride ldx (elements); y: [M][C] contiguous. */
 int ccedit_layernorm(const void* x, int64_t ldx, void* y, const float* gamma, const float* beta, int64_t M, int32_t C,
                      float eps, void* stream);
+/* Row statistics only: stats[m] = (mean, 1/sqrt(var + eps)) as fp32 pairs.  Used when the LayerNorm is folded into the
+ * GEMM that consumes it (ccedit_gemm_desc.rowstats): LN(x) W^T = rstd (x (gamma o W)^T - mean colsum(gamma o W)) + beta W^T. */
+int ccedit_layernorm_stats(const void* x, int64_t ldx, float* stats, int64_t M, int32_t C, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Attention (F.scaled_dot_product_attention call site attention.py:444-448; scale = d^-1/2; 8 heads typical).

@@ -117,6 +117,40 @@ def test_conv3x3(ops, Fr, H, W, Cin, Cout, emb, silu):
     close(out[..., :Cout].permute(0, 3, 1, 2), ref, f"conv3x3 {Cin}->{Cout}")
 
 
+@pytest.mark.parametrize("M,K,N,geglu,bias", [(5000, 320, 320, False, False), (3001, 320, 960, False, False),
+                                               (4000, 320, 2560, True, True), (700, 1280, 10240, True, True),
+                                               (2000, 640, 640, False, True), (130, 1280, 3840, False, False)])
+def test_linear_with_folded_layernorm(ops, M, K, N, geglu, bias):
+    """attention.py:667-669 + to_q / to_k / to_v / ff.net.0: LayerNorm folded into the consuming GEMM - statistics pass
+    (ccedit_layernorm_stats) + gamma-scaled weight + per-row epilogue - against F.layer_norm + F.linear in fp32.  The rows
+    carry a large common offset so that the mean term really has to cancel."""
+    g = torch.Generator().manual_seed(70)
+    x = (torch.randn(M, K, generator=g) * 1.5 + 3.0 * torch.randn(M, 1, generator=g)).half()
+    w = rnd(N, K, seed=71, scale=1 / math.sqrt(K))
+    b = rnd(N, seed=72).float() if bias else None
+    gamma, beta = 1 + 0.3 * rnd(K, seed=73).float(), 0.2 * rnd(K, seed=74).float()
+    pw = ops.pack_weight(w.float(), b, "cuda", geglu=geglu, ln_gamma=gamma, ln_beta=beta)
+    xc = x.cuda()
+    st = ops.layernorm_stats(xc)
+    ref_mean, ref_var = x.float().mean(1), x.float().var(1, unbiased=False)
+    close(st[:, 0], ref_mean, "row mean", rtol=1e-5, atol=1e-5)
+    close(st[:, 1], (ref_var + 1e-5).rsqrt(), "row rstd", rtol=1e-5, atol=1e-5)
+    out = ops.gemm(xc, pw, torch.empty(M, pw.n_out, dtype=torch.float16, device="cuda"), rowstats=st)
+    # identical fp16-rounded operands (see the module docstring): the kernel's weight operand is fp16(gamma o W)
+    xhat = F.layer_norm(x.float(), (K,))
+    ref = F.linear(xhat, (w.float() * gamma[None, :]).half().float(), (w.float() @ beta) + (0 if b is None else b))
+    if geglu:
+        v, gt = ref.chunk(2, dim=-1)
+        ref = v * F.gelu(gt)
+    close(out, ref, f"LN-folded linear {M}x{K}x{N} geglu={geglu}")
+    # and against the un-fused fp32 formulation: only the rounding of gamma o W to fp16 separates the two
+    full = F.linear(F.layer_norm(x.float(), (K,), gamma, beta), w.float(), b)
+    if geglu:
+        v, gt = full.chunk(2, dim=-1)
+        full = v * F.gelu(gt)
+    assert float((out.float().cpu() - full).abs().max()) <= 4e-3 * max(1.0, float(full.abs().max()))
+
+
 @pytest.mark.parametrize("Fr,H,W", [(2, 32, 128), (1, 40, 70), (3, 16, 64), (1, 5, 9)])
 def test_hint_stem_first_two_layers_fused(ops, Fr, H, W):
     """controlmodel.py:215-219: conv3x3(3->16)+SiLU+conv3x3(16->16)+SiLU in one kernel (csrc/hint_stem.cu), ragged tiles."""

@@ -30,9 +30,9 @@ def check(Fr, L, Lkv, heads, d, scale=1.0):
           f"{'OK' if err < 2e-3 * max(1.0, r.abs().max().item()) else 'BAD'}", flush=True)
 
 
-def bench(Fr, L, heads, d, iters=5):
+def bench(Fr, L, heads, d, iters=5, scale=1.0):
     C = heads * d
-    qkv = torch.randn(Fr, L, 3 * C, device=dev).half()
+    qkv = (torch.randn(Fr, L, 3 * C, device=dev) * scale).half()
     out = torch.empty(Fr, L, C, dtype=torch.float16, device=dev)
     run = lambda: ops.attention(qkv[..., :C], [ops.KVSegment(qkv[..., C:2 * C], qkv[..., 2 * C:])], heads, out)
     run()
@@ -44,7 +44,7 @@ def bench(Fr, L, heads, d, iters=5):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    print(f"attn F={Fr} L={L} d={d}: {ms:8.3f} ms  {4.0 * Fr * L * L * C / ms / 1e9:8.1f} TFLOP/s", flush=True)
+    print(f"attn F={Fr} L={L} d={d} scale={scale}: {ms:8.3f} ms  {4.0 * Fr * L * L * C / ms / 1e9:8.1f} TFLOP/s", flush=True)
 
 
 def trace():
@@ -69,6 +69,10 @@ def trace():
 
 
 if __name__ == "__main__":
+    if os.environ.get("CCEDIT_ATTN_SCALES"):
+        for sc in (0.5, 1.0, 2.0, 3.0, 4.0, 6.0):
+            bench(34, 6144, 8, 40, scale=sc)
+        sys.exit(0)
     if os.environ.get("CCEDIT_ATTN_TRACE"):
         trace()
         sys.exit(0)
