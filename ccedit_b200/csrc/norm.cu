@@ -6,6 +6,7 @@
 #include "../../include/ccedit_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace ccedit {
 extern std::atomic<long long> g_launch_count;
@@ -162,6 +163,146 @@ __global__ void gn_spatial_apply_kernel(const __half* __restrict__ x, __half* __
   for (; r < row_end; r += rpi) {
     float v[8];
     unpack8(__ldg(xb + static_cast<size_t>(r) * nvec), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j] * sc[j] + sh[j];
+      v[j] = silu ? silu_f(t) : t;
+    }
+    yb[static_cast<size_t>(r) * nvec] = pack8(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// spatial GroupNorm, single pass over HBM: statistics and apply in ONE kernel.  grid (nsplit, F) with every CTA resident
+// at the same time (the host sizes nsplit from the occupancy); CTA (s, f) reduces its slice of frame f, publishes the
+// partial sums, waits on a per-frame arrival counter until the nsplit slices of the frame are in, and then normalises
+// the SAME slice - walking it backwards, so that the rows it read last (still in L2) are re-read first.  The two-kernel
+// version above reads the tensor twice from HBM at the big levels (134 MB per activation > L2 once all frames are in
+// flight); here the second read is an L2 hit for most of the slice.  Statistics stay deterministic (fixed-order sums).
+// counters: [F][2] ints, zero before the first launch; the last CTA to leave a frame's barrier resets them.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gn_spatial_fused_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        float* __restrict__ partial, int* __restrict__ counters, int HW, int C, int nvec,
+                                        int rpi, float eps, int silu) {
+  extern __shared__ float gn_sm[];            // [2][rpi][C]
+  __shared__ float smean[kGroups], srstd[kGroups];
+  float* ssum = gn_sm;
+  float* ssq = gn_sm + rpi * C;
+  const int f = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+  const int cv = threadIdx.x % nvec, r0 = threadIdx.x / nvec;
+  const int rows_per_split = (HW + nsplit - 1) / nsplit;
+  const int row_begin = split * rows_per_split;
+  const int row_end = min(HW, row_begin + rows_per_split);
+  const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<size_t>(f) * HW * C) + cv;
+  {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    int r = row_begin + r0;
+    for (; r + 3 * rpi < row_end; r += 4 * rpi) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(xb + static_cast<size_t>(r + k * rpi) * nvec);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v[8];
+        unpack8(u[k], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[j];
+          q[j] += v[j] * v[j];
+        }
+      }
+    }
+    for (; r < row_end; r += rpi) {
+      float v[8];
+      unpack8(__ldg(xb + static_cast<size_t>(r) * nvec), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] += v[j] * v[j];
+      }
+    }
+    park_channels(s, q, ssum, ssq, r0, C, cv * 8);
+  }
+  __syncthreads();
+  if (threadIdx.x < kGroups) {
+    const int cpg = C / kGroups, g = threadIdx.x;
+    float ts = 0.f, tq = 0.f;
+    for (int r = 0; r < rpi; ++r)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        ts += ssum[r * C + c];
+        tq += ssq[r * C + c];
+      }
+    float* pp = partial + (static_cast<size_t>(f) * nsplit + split) * 2 * kGroups;
+    pp[2 * g] = ts;
+    pp[2 * g + 1] = tq;
+    __threadfence();                                       // the partial sums are visible before the arrival below
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&counters[2 * f], 1);
+    unsigned spins = 0;
+    while (atomicAdd(&counters[2 * f], 0) < nsplit) {      // all slices of this frame
+      __nanosleep(64);
+      if (++spins > (1u << 24)) __trap();                  // a scheduling assumption broke: fail instead of hanging
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x < kGroups) {
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < nsplit; ++k) {
+      const float* pp = partial + (static_cast<size_t>(f) * nsplit + k) * 2 * kGroups;
+      s += __ldcg(pp + 2 * threadIdx.x);
+      q += __ldcg(pp + 2 * threadIdx.x + 1);
+    }
+    const float n = static_cast<float>(HW) * static_cast<float>(C / kGroups);
+    const float mean = s / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    smean[threadIdx.x] = mean;
+    srstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                                  // leave the barrier; the last one out re-arms it
+    if (atomicAdd(&counters[2 * f + 1], 1) == nsplit - 1) {
+      counters[2 * f] = 0;
+      counters[2 * f + 1] = 0;
+    }
+  }
+  const int cpg = C / kGroups;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float a = srstd[g] * gamma[c];
+    sc[j] = a;
+    sh[j] = beta[c] - smean[g] * a;
+  }
+  uint4* yb = reinterpret_cast<uint4*>(y + static_cast<size_t>(f) * HW * C) + cv;
+  // backwards over the slice, four rows in flight per thread
+  int r = row_end - 1 - r0;
+  for (; r - 3 * rpi >= row_begin; r -= 4 * rpi) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldcg(xb + static_cast<size_t>(r - k * rpi) * nvec);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      unpack8(u[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = v[j] * sc[j] + sh[j];
+        v[j] = silu ? silu_f(t) : t;
+      }
+      yb[static_cast<size_t>(r - k * rpi) * nvec] = pack8(v);
+    }
+  }
+  for (; r >= row_begin; r -= rpi) {
+    float v[8];
+    unpack8(__ldcg(xb + static_cast<size_t>(r) * nvec), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float t = v[j] * sc[j] + sh[j];
@@ -378,10 +519,34 @@ extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gam
   const int nvec = C / 8, rpi = pick_rpi(nvec);
   const int threads = nvec * rpi;
   long long bytes = static_cast<long long>(HW) * C * 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // ---- single-pass kernel when the whole grid can be resident at once (it synchronises the slices of a frame) ----
+  {
+    const size_t smem = 2 * static_cast<size_t>(rpi) * C * sizeof(float);
+    int per_sm = 0;
+    const int sms = device_sm_count();
+    static const bool disabled = [] { const char* e = getenv("CCEDIT_GN_FUSED"); return e && atoi(e) == 0; }();
+    if (!disabled && sms > 0 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_spatial_fused_kernel, threads, smem) == cudaSuccess) {
+      const long long capacity = static_cast<long long>(per_sm) * sms * 4 / 5;   // margin: the barrier needs co-residency
+      int nsplit = static_cast<int>(capacity / F);
+      const int want = static_cast<int>(bytes / 16384) > 0 ? static_cast<int>(bytes / 16384) : 1;   // >= 16 KB per slice
+      if (nsplit > want) nsplit = want;
+      if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+      if (nsplit >= 1) {
+        int* counters = reinterpret_cast<int*>(partial + static_cast<size_t>(F) * kMaxSplit * 2 * kGroups);
+        gn_spatial_fused_kernel<<<dim3(nsplit, F), threads, smem, st>>>(
+            static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, partial, counters, HW, C, nvec, rpi, eps,
+            silu);
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_spatial(fused)");
+        return CCEDIT_OK;
+      }
+    }
+  }
   int nsplit = static_cast<int>(bytes / 65536);
   if (nsplit < 1) nsplit = 1;
   if (nsplit > kMaxSplit) nsplit = kMaxSplit;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   gn_spatial_stats_kernel<<<dim3(nsplit, F), threads, 2 * rpi * C * sizeof(float), st>>>(
       static_cast<const __half*>(x), partial, HW, C, nvec, rpi, nsplit);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_spatial(stats)");

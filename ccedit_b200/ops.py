@@ -298,10 +298,10 @@ _GN_SCRATCH = {}
 
 def _gn_scratch(device, F: int) -> torch.Tensor:
     key = (device, torch.cuda.current_stream().cuda_stream)
-    need = F * 32 * 64
+    need = F * 32 * 64 + 2 * F            # partial sums [F][32][32][2] + the single-pass kernel's arrival counters [F][2]
     buf = _GN_SCRATCH.get(key)
     if buf is None or buf.numel() < need:
-        buf = torch.empty(need, dtype=torch.float32, device=device)
+        buf = torch.zeros(need, dtype=torch.float32, device=device)   # the counters must start at zero (self re-arming)
         _GN_SCRATCH[key] = buf
     return buf
 

@@ -101,7 +101,9 @@ int ccedit_gemm_trace(int64_t* device_buf);
  *                   temporal = per pixel over (C/32)*T   (openaimodel.py:157)
  * LayerNorm(C) per token (attention.py:667-669, 749-750).
  * ------------------------------------------------------------------------------------------------------------------ */
-/* x,y: [F][HW][C]; partial: fp32 scratch [F][nsplit][32][2]; gamma/beta fp32 [C]. silu!=0 fuses SiLU. */
+/* x,y: [F][HW][C]; gamma/beta fp32 [C]; silu!=0 fuses SiLU.  partial: fp32 scratch of F*(32*64 + 2) elements, private to
+ * the stream: [F][32][32][2] partial sums followed by F*2 int32 arrival counters that must be ZERO before the first call
+ * (the single-pass kernel re-arms them itself; it is used whenever all of its CTAs can be resident at once). */
 int ccedit_groupnorm_spatial(const void* x, void* y, const float* gamma, const float* beta, float* partial,
                              int32_t F, int32_t HW, int32_t C, float eps, int32_t silu, void* stream);
 /* x,y: [B][T][HW][C]; statistics over (C/32, T) for every (b, hw). */
