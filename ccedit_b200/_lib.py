@@ -46,6 +46,7 @@ class GemmDesc(C.Structure):
         ("flags", C.c_int32),
         ("rowstats", C.c_void_p),
         ("colsum", C.c_void_p),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -77,6 +78,7 @@ SIGNATURES = {
     "ccedit_groupnorm_temporal": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "ccedit_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
     "ccedit_layernorm_stats": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp]),
+    "ccedit_layernorm_stats_combine": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _f32, _vp]),
     "ccedit_attention": (C.c_int, [C.POINTER(AttnDesc), _vp]),
     "ccedit_temporal_attention": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32,
                                             _f32, _vp]),

@@ -68,6 +68,9 @@ struct GemmKParams {
   // LayerNorm folded into the epilogue (template flag LNF): out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]
   const float2* rowstats;
   const float* colsum;
+  // Row statistics of THIS GEMM's output for the LayerNorm that follows it: per row and per (n-tile, column half) the
+  // epilogue thread writes (sum, sum of squares) of its final fp32 values to stats_out[(m * 2 * n_tiles + slot)].
+  float2* stats_out;
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -243,6 +246,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
     tcgen05_fence_after();
     if (tracing && titer < 64) p.trace[16 * titer + 2] = clock64();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * kAccStride);
+    float st_s = 0.f, st_q = 0.f;                             // stats_out: this thread's partial row sums
 
 #pragma unroll 1
     for (int ci = eg; ci < nchunks; ci += 2) {
@@ -299,6 +303,13 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
         }
         if (NRES >= 1) add_res(v, c1);
         if (NRES >= 2) add_res(v, c2);
+        if (MODE == kModePlain && p.stats_out) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            st_s += v[j];
+            st_q = fmaf(v[j], v[j], st_q);
+          }
+        }
         uint4 s0, s1;
         s0.x = pack_half2(v[0], v[1]);
         s0.y = pack_half2(v[2], v[3]);
@@ -315,6 +326,8 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
       if (NRES >= 1) { c1[0] = n1[0]; c1[1] = n1[1]; }
       if (NRES >= 2) { c2[0] = n2[0]; c2[1] = n2[1]; }
     }
+    if (MODE == kModePlain && p.stats_out && valid)
+      p.stats_out[static_cast<long long>(dig[1] * p.box[0] + l[0]) * (2 * p.n_tiles) + 2 * n_tile + eg] = make_float2(st_s, st_q);
     if (tracing && titer < 64) p.trace[16 * titer + 3] = clock64();
     tcgen05_fence_before();
     __syncwarp();
@@ -500,6 +513,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
     __syncwarp();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * kAccStride) +
                            static_cast<uint32_t>(eg * W);
+    float st_s = 0.f, st_q = 0.f;                             // stats_out: this thread's partial row sums
 
 #pragma unroll 1
     for (int ci = 0; ci < nch; ++ci) {
@@ -563,6 +577,13 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
       }
       if (NRES >= 1) add_res(v, c1);
       if (NRES >= 2 && valid) add_res(v, c2);
+      if (MODE == kModePlain && p.stats_out) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          st_s += v[j];
+          st_q = fmaf(v[j], v[j], st_q);
+        }
+      }
       uint4 q0, q1;
       q0.x = pack_half2(v[0], v[1]);
       q0.y = pack_half2(v[2], v[3]);
@@ -576,6 +597,8 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
       *s1 = q1;
       if (NRES >= 2) { c2[0] = n2[0]; c2[1] = n2[1]; }
     }
+    if (MODE == kModePlain && p.stats_out && valid)
+      p.stats_out[static_cast<long long>(dig[1] * p.box[0] + l[0]) * (2 * p.n_tiles) + 2 * n_tile + eg] = make_float2(st_s, st_q);
     if (tracing && it < 64) p.trace[16 * it + 3] = clock64();
     tcgen05_fence_before();
     fence_proxy_async_smem();                                // this thread's staging writes -> visible to the TMA store
@@ -977,6 +1000,12 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     return CCEDIT_ERR_CUDA;
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (d->stats_out) {
+    CCEDIT_CHECK_ARG(!geglu && !(d->flags & CCEDIT_GEMM_SILU) && d->out_dims[1] == 1 && d->out_dims[2] == 1 && d->out_dims[3] == 1,
+                     "ccedit_gemm: stats_out needs a plain 2-D [M, C] GEMM");
+    CCEDIT_CHECK_ARG((reinterpret_cast<uintptr_t>(d->stats_out) & 7) == 0, "ccedit_gemm: stats_out must be 8-byte aligned");
+    p.stats_out = reinterpret_cast<float2*>(d->stats_out);
+  }
   cudaError_t err;
   const bool lnf = d->rowstats != nullptr;
   CCEDIT_CHECK_ARG((d->rowstats != nullptr) == (d->colsum != nullptr), "ccedit_gemm: rowstats and colsum go together");

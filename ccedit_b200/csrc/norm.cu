@@ -14,6 +14,7 @@ int device_sm_count();
 
 constexpr int kGroups = 32;
 constexpr int kMaxSplit = 32;
+constexpr int kGnCounterFloats = 8192;       // head of the spatial-GroupNorm scratch: per-frame arrival counters (zeroed once)
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -533,11 +534,11 @@ extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gam
       const int want = static_cast<int>(bytes / 16384) > 0 ? static_cast<int>(bytes / 16384) : 1;   // >= 16 KB per slice
       if (nsplit > want) nsplit = want;
       if (nsplit > kMaxSplit) nsplit = kMaxSplit;
-      if (nsplit >= 1) {
-        int* counters = reinterpret_cast<int*>(partial + static_cast<size_t>(F) * kMaxSplit * 2 * kGroups);
+      if (nsplit >= 1 && 2 * F <= kGnCounterFloats) {
+        int* counters = reinterpret_cast<int*>(partial);      // fixed place: [kGnCounterFloats] ints ahead of the partial sums
         gn_spatial_fused_kernel<<<dim3(nsplit, F), threads, smem, st>>>(
-            static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, partial, counters, HW, C, nvec, rpi, eps,
-            silu);
+            static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, partial + kGnCounterFloats, counters, HW, C,
+            nvec, rpi, eps, silu);
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_spatial(fused)");
         return CCEDIT_OK;
@@ -547,6 +548,7 @@ extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gam
   int nsplit = static_cast<int>(bytes / 65536);
   if (nsplit < 1) nsplit = 1;
   if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+  partial += kGnCounterFloats;
   gn_spatial_stats_kernel<<<dim3(nsplit, F), threads, 2 * rpi * C * sizeof(float), st>>>(
       static_cast<const __half*>(x), partial, HW, C, nvec, rpi, nsplit);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_spatial(stats)");
@@ -702,5 +704,37 @@ extern "C" int ccedit_layernorm_stats(const void* x, int64_t ldx, float* stats, 
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_layernorm_stats");
+  return CCEDIT_OK;
+}
+
+// (sum, sum of squares) partials written by the producing GEMM's epilogue (ccedit_gemm_desc.stats_out) -> (mean, rstd).
+namespace ccedit {
+__global__ void layernorm_combine_kernel(const float2* __restrict__ partial, int P, long long M, float invc, float eps,
+                                         float2* __restrict__ stats) {
+  const long long m = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float s = 0.f, q = 0.f;
+  for (int k = 0; k < P; ++k) {
+    const float2 v = __ldg(partial + m * P + k);
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s * invc;
+  const float var = fmaxf(fmaf(-mean, mean, q * invc), 0.f);
+  stats[m] = make_float2(mean, rsqrtf(var + eps));
+}
+}  // namespace ccedit
+
+extern "C" int ccedit_layernorm_stats_combine(const float* partial, int32_t P, float* stats, int64_t M, int32_t C,
+                                              float eps, void* stream) {
+  using namespace ccedit;
+  CCEDIT_CHECK_ARG(partial && stats && P >= 1 && P <= 64 && M > 0 && C > 0, "ccedit_layernorm_stats_combine: bad arguments");
+  CCEDIT_CHECK_ARG(((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(stats)) & 7) == 0,
+                   "ccedit_layernorm_stats_combine: pointers must be 8-byte aligned");
+  const int threads = 256;
+  layernorm_combine_kernel<<<static_cast<unsigned>((M + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(partial), P, M, 1.f / static_cast<float>(C), eps, reinterpret_cast<float2*>(stats));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_layernorm_stats_combine");
   return CCEDIT_OK;
 }

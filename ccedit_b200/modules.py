@@ -197,21 +197,28 @@ class BasicTransformerBlock(nn.Module):
         self.attn2 = CrossAttention(dim, context_dim, n_heads, d_head)
         self.norm1, self.norm2, self.norm3 = norm(dim), norm(dim), norm(dim)
 
-    def run(self, x, F, L, ctx: Ctx):
+    def run(self, x, F, L, ctx: Ctx, sp=None):
+        """sp: (sum, sum of squares) partials of x written by the GEMM that produced it (ops.gemm(stats_out=)), or None."""
         dev, C, M = x.device, x.shape[1], x.shape[0]
         heads = self.attn1.heads
-        # the three LayerNorms are folded into the GEMMs they feed: one statistics pass each (ops.layernorm_stats)
-        st = ops.layernorm_stats(x)
+        # The three LayerNorms are folded into the GEMMs they feed.  Their row statistics come from the epilogue of the
+        # GEMM that produced x (proj_in, attn1.to_out, attn2.to_out) - no pass over the activation at all - or, when the
+        # caller has none, from one statistics pass (ops.layernorm_stats).
+        st = ops.layernorm_stats(x) if sp is None else ops.layernorm_stats_combine(sp, C)
         qkv = ops.gemm(x, self.attn1.fused(dev, "qkv", ln=self.norm1), _new(x, M, 3 * C), rowstats=st)
         q3 = qkv.view(F, L, 3 * C)
         att = ops.attention(q3[..., :C], [KVSegment(q3[..., C:2 * C], q3[..., 2 * C:])], heads, _new(x, F, L, C))
-        x = ops.gemm(att.view(M, C), self.attn1.to_out["0"].packed(dev), _new(x, M, C), res1=x)
-        ops.layernorm_stats(x, out=st)
+        o1 = self.attn1.to_out["0"].packed(dev)
+        sp = torch.empty(M, ops.stats_slots(o1), 2, dtype=torch.float32, device=dev)
+        x = ops.gemm(att.view(M, C), o1, _new(x, M, C), res1=x, stats_out=sp)
+        ops.layernorm_stats_combine(sp, C, out=st)
         q = ops.gemm(x, self.attn2.to_q.packed_ln(dev, self.norm2), _new(x, M, C), rowstats=st)
         k, v = ctx.text_kv[id(self.attn2)]
         att = ops.attention(q.view(F, L, C), [KVSegment(k, v, div=ctx.T)], heads, att)
-        x = ops.gemm(att.view(M, C), self.attn2.to_out["0"].packed(dev), _new(x, M, C), res1=x)
-        ops.layernorm_stats(x, out=st)
+        o2 = self.attn2.to_out["0"].packed(dev)
+        sp2 = sp if ops.stats_slots(o2) == sp.shape[1] else torch.empty(M, ops.stats_slots(o2), 2, dtype=torch.float32, device=dev)
+        x = ops.gemm(att.view(M, C), o2, _new(x, M, C), res1=x, stats_out=sp2)
+        ops.layernorm_stats_combine(sp2, C, out=st)
         return self.ff.run(x, self.norm3, st)
 
 
@@ -224,15 +231,18 @@ class BasicTransformerSingleLayerBlock(nn.Module):
         self.ff = FeedForward(dim)
         self.norm1, self.norm2 = norm(dim), norm(dim)
 
-    def run(self, x, attend, out=None):
-        """x: tokens [M, C]; attend(q [M,C], kv [M,2C]) -> [M, C] runs the attention of the calling layer."""
+    def run(self, x, attend, out=None, sp=None):
+        """x: tokens [M, C]; attend(q [M,C], kv [M,2C]) -> [M, C] runs the attention of the calling layer; sp: statistics
+        partials of x from the GEMM that produced it (see BasicTransformerBlock.run)."""
         dev, C, M = x.device, x.shape[1], x.shape[0]
-        st = ops.layernorm_stats(x)
+        st = ops.layernorm_stats(x) if sp is None else ops.layernorm_stats_combine(sp, C)
         q = ops.gemm(x, self.attn1.to_q.packed_ln(dev, self.norm1), _new(x, M, C), rowstats=st)
         kv = ops.gemm(x, self.attn1.fused(dev, "kv"), _new(x, M, 2 * C))
         att = attend(q, kv)
-        x = ops.gemm(att, self.attn1.to_out["0"].packed(dev), _new(x, M, C), res1=x)
-        ops.layernorm_stats(x, out=st)
+        o1 = self.attn1.to_out["0"].packed(dev)
+        sp = torch.empty(M, ops.stats_slots(o1), 2, dtype=torch.float32, device=dev)
+        x = ops.gemm(att, o1, _new(x, M, C), res1=x, stats_out=sp)
+        ops.layernorm_stats_combine(sp, C, out=st)
         return self.ff.run(x, self.norm2, st, out)
 
 
@@ -261,16 +271,18 @@ class SpatialTransformer(nn.Module):
         F, H, W, C = x4.shape
         L, M = H * W, F * H * W
         xn = ops.groupnorm_spatial(x4, *self.norm.affine(dev), GN_EPS_ATTN, False)
-        h = ops.gemm(xn.view(M, C), self.proj_in.packed(dev), _new(x4, M, C))
+        pin = self.proj_in.packed(dev)
+        sp = torch.empty(M, ops.stats_slots(pin), 2, dtype=torch.float32, device=dev)   # LayerNorm statistics of h
+        h = ops.gemm(xn.view(M, C), pin, _new(x4, M, C), stats_out=sp)
         blk = self.transformer_blocks[0]
         if self.disable_text_ca:
             def attend(q, kv):
                 kv3 = kv.view(F, L, 2 * C)
                 return ops.attention(q.view(F, L, C), [KVSegment(kv3[..., :C], kv3[..., C:])], self.heads,
                                      _new(q, F, L, C)).view(M, C)
-            h = blk.run(h, attend)
+            h = blk.run(h, attend, sp=sp)
         else:
-            h = blk.run(h, F, L, ctx)
+            h = blk.run(h, F, L, ctx, sp=sp)
         out = _new(x4, F, H, W, C) if out is None else out
         ops.gemm(h, self.proj_out.packed(dev), out.view(M, C) if out.is_contiguous() else out.flatten(0, 2),
                  res1=x4.view(M, C))
@@ -306,14 +318,16 @@ class SpatialTransformer3D(SpatialTransformer):
         xs = self.run_spatial(x5.view(F, H, W, C), ctx)                     # [F,H,W,C]
         # ---- temporal attention over T per pixel (attention.py:1172-1207) ----
         xt = ops.groupnorm_temporal(xs.view(B, T, L, C), *self.norm_temporal.affine(dev), GN_EPS_ATTN, False)
-        p = ops.gemm(xt.view(M, C), self.proj_in_temporal.packed(dev), _new(x5, M, C))
+        pin = self.proj_in_temporal.packed(dev)
+        sp = torch.empty(M, ops.stats_slots(pin), 2, dtype=torch.float32, device=dev)
+        p = ops.gemm(xt.view(M, C), pin, _new(x5, M, C), stats_out=sp)
 
         def attend_t(q, kv):
             kv4 = kv.view(B, T, L, 2 * C)
             return ops.temporal_attention(q.view(B, T, L, C), kv4[..., :C], kv4[..., C:], heads,
                                           _new(q, B, T, L, C)).view(M, C)
 
-        p = self.transformer_blocks_temporal[0].run(p, attend_t)
+        p = self.transformer_blocks_temporal[0].run(p, attend_t, sp=sp)
         last = self.ca_type is None
         dst = (_new(x5, M, C) if out is None else _as2d(out, M, C)) if last else _new(x5, M, C)
         ops.gemm(p, self.proj_out_temporal.packed(dev), dst, res1=xs.view(M, C))
@@ -322,7 +336,9 @@ class SpatialTransformer3D(SpatialTransformer):
         # ---- cross-frame attention (SpatialTransformer3DCA.forward, attention.py:1302-1350) ----
         x2 = dst                                                               # [M, C] contiguous
         xc = ops.groupnorm_spatial(x2.view(F, L, C), *self.norm_temporal_ca.affine(dev), GN_EPS_ATTN, False)
-        p = ops.gemm(xc.view(M, C), self.proj_in_temporal_ca.packed(dev), _new(x5, M, C))
+        pin = self.proj_in_temporal_ca.packed(dev)
+        sp = torch.empty(M, ops.stats_slots(pin), 2, dtype=torch.float32, device=dev)
+        p = ops.gemm(xc.view(M, C), pin, _new(x5, M, C), stats_out=sp)
 
         def attend_ca(q, kv):
             kv3 = kv.view(F, L, 2 * C)
@@ -332,7 +348,7 @@ class SpatialTransformer3D(SpatialTransformer):
             segs = {"center": [center], "self": [own], "center_self": [center, own]}[self.ca_type]
             return ops.attention(q.view(F, L, C), segs, heads, _new(q, F, L, C)).view(M, C)
 
-        p = self.transformer_blocks_temporal_ca[0].run(p, attend_ca)
+        p = self.transformer_blocks_temporal_ca[0].run(p, attend_ca, sp=sp)
         dst = _new(x5, M, C) if out is None else _as2d(out, M, C)
         ops.gemm(p, self.proj_out_temporal_ca.packed(dev), dst, res1=x2)
         return dst.view(B, T, H, W, C) if out is None else out

@@ -218,7 +218,8 @@ def _dims_strides(t: torch.Tensor):
 def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = ONE_TAP, *,
          rowbias: Optional[torch.Tensor] = None, rb_dim: int = 0, rb_div: int = 1,
          res1: Optional[torch.Tensor] = None, res2: Optional[torch.Tensor] = None, silu: bool = False,
-         box: Optional[tuple] = None, rowstats: Optional[torch.Tensor] = None) -> torch.Tensor:
+         box: Optional[tuple] = None, rowstats: Optional[torch.Tensor] = None,
+         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[p, :] = epi( sum_tap A[p + tap, :] @ W[:, tap, :]^T ).  a/out/res*: [d4, d3, d2, d1, C] views (C contiguous)."""
     _require(a, name="a")
     _require(out, name="out")
@@ -279,6 +280,11 @@ def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = 
             raise RuntimeError(f"ccedit_b200.gemm: rowstats must be contiguous [{odims[0]}, 2]")
         d.rowstats = rowstats.data_ptr()
         d.colsum = pw.colsum.data_ptr()
+    if stats_out is not None:
+        _require(stats_out, torch.float32, "stats_out")
+        if tuple(stats_out.shape) != (odims[0], stats_slots(pw), 2) or not stats_out.is_contiguous():
+            raise RuntimeError(f"ccedit_b200.gemm: stats_out must be contiguous [{odims[0]}, {stats_slots(pw)}, 2]")
+        d.stats_out = stats_out.data_ptr()
     m_rows = math.prod(odims)
     kind = {1: "gemm.linear", 3: "gemm.temporal_k3", 9: "gemm.conv3x3"}.get(len(taps), "gemm.other")
     if pw.geglu:
@@ -298,7 +304,7 @@ _GN_SCRATCH = {}
 
 def _gn_scratch(device, F: int) -> torch.Tensor:
     key = (device, torch.cuda.current_stream().cuda_stream)
-    need = F * 32 * 64 + 2 * F            # partial sums [F][32][32][2] + the single-pass kernel's arrival counters [F][2]
+    need = 8192 + F * 32 * 64             # the single-pass kernel's arrival counters (fixed 8192 slots) + partial sums [F][32][32][2]
     buf = _GN_SCRATCH.get(key)
     if buf is None or buf.numel() < need:
         buf = torch.zeros(need, dtype=torch.float32, device=device)   # the counters must start at zero (self re-arming)
@@ -354,6 +360,22 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     out = torch.empty(x.shape, dtype=torch.float16, device=x.device) if out is None else out
     _call("layernorm" + (f"[M={M},C={Cc}]" if _PROF_SHAPES else ""), _lib.load().ccedit_layernorm,
           (x2.data_ptr(), ldx, out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M, Cc, eps, _stream()), nbytes=2 * _nb(out))
+    return out
+
+
+def stats_slots(pw: PackedWeight) -> int:
+    """Partial-statistics slots per row a GEMM with this weight writes (``gemm(stats_out=)``): 2 per N tile."""
+    return 2 * (pw.n // pw.bn)
+
+
+def layernorm_stats_combine(partial: torch.Tensor, C: int, eps: float = 1e-5, out: Optional[torch.Tensor] = None
+                            ) -> torch.Tensor:
+    """partial: fp32 [M, P, 2] (sum, sum of squares) from ``gemm(stats_out=)`` over C channels -> fp32 [M, 2] (mean, rstd)."""
+    _require(partial, torch.float32, "partial")
+    M, P, _ = partial.shape
+    out = torch.empty(M, 2, dtype=torch.float32, device=partial.device) if out is None else out
+    _call("layernorm_stats_combine", _lib.load().ccedit_layernorm_stats_combine,
+          (partial.data_ptr(), P, out.data_ptr(), M, C, eps, _stream()), nbytes=_nb(partial, out))
     return out
 
 

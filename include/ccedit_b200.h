@@ -86,6 +86,11 @@ typedef struct ccedit_gemm_desc {
    * colsum: fp32 [n] = sum_k fp16(W[n][k]).  Both NULL => no fold.  Not combinable with rowbias / residuals. */
   const float* rowstats;
   const float* colsum;
+  /* Statistics of THIS GEMM's output for the LayerNorm that consumes it (the next layer's rowstats without another
+   * pass over the activation): fp32 [M][P][2] with P = 2 * n / bn; every epilogue thread writes (sum, sum of squares) of
+   * the final fp32 values of its row over its column range.  ccedit_layernorm_stats_combine turns them into (mean, rstd).
+   * Plain 2-D GEMMs only (no GEGLU / SiLU).  NULL => off. */
+  float* stats_out;
 } ccedit_gemm_desc;
 
 int ccedit_gemm(const ccedit_gemm_desc* d, void* stream);
@@ -101,9 +106,9 @@ int ccedit_gemm_trace(int64_t* device_buf);
  *                   temporal = per pixel over (C/32)*T   (openaimodel.py:157)
  * LayerNorm(C) per token (attention.py:667-669, 749-750).
  * ------------------------------------------------------------------------------------------------------------------ */
-/* x,y: [F][HW][C]; gamma/beta fp32 [C]; silu!=0 fuses SiLU.  partial: fp32 scratch of F*(32*64 + 2) elements, private to
- * the stream: [F][32][32][2] partial sums followed by F*2 int32 arrival counters that must be ZERO before the first call
- * (the single-pass kernel re-arms them itself; it is used whenever all of its CTAs can be resident at once). */
+/* x,y: [F][HW][C]; gamma/beta fp32 [C]; silu!=0 fuses SiLU.  partial: fp32 scratch of 8192 + F*32*64 elements, private to
+ * the stream: 8192 int32 arrival counters (2 per frame) that must be ZERO before the first call - the single-pass kernel,
+ * used whenever all of its CTAs can be resident at once, re-arms them itself - followed by [F][32][32][2] partial sums. */
 int ccedit_groupnorm_spatial(const void* x, void* y, const float* gamma, const float* beta, float* partial,
                              int32_t F, int32_t HW, int32_t C, float eps, int32_t silu, void* stream);
 /* x,y: [B][T][HW][C]; statistics over (C/32, T) for every (b, hw). */
@@ -115,6 +120,9 @@ int ccedit_layernorm(const void* x, int64_t ldx, void* y, const float* gamma, co
 /* Row statistics only: stats[m] = (mean, 1/sqrt(var + eps)) as fp32 pairs.  Used when the LayerNorm is folded into the
  * GEMM that consumes it (ccedit_gemm_desc.rowstats): LN(x) W^T = rstd (x (gamma o W)^T - mean colsum(gamma o W)) + beta W^T. */
 int ccedit_layernorm_stats(const void* x, int64_t ldx, float* stats, int64_t M, int32_t C, float eps, void* stream);
+/* partial: fp32 [M][P][2] written by ccedit_gemm (stats_out) for an activation of C channels -> stats [M][2]. */
+int ccedit_layernorm_stats_combine(const float* partial, int32_t P, float* stats, int64_t M, int32_t C, float eps,
+                                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Attention (F.scaled_dot_product_attention call site attention.py:444-448; scale = d^-1/2; 8 heads typical).

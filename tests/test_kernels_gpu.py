@@ -151,6 +151,24 @@ def test_linear_with_folded_layernorm(ops, M, K, N, geglu, bias):
     assert float((out.float().cpu() - full).abs().max()) <= 4e-3 * max(1.0, float(full.abs().max()))
 
 
+@pytest.mark.parametrize("M,K,N,res", [(5000, 320, 320, True), (3001, 640, 640, False), (2000, 1280, 1280, True),
+                                        (777, 2560, 640, True), (300, 320, 96, False)])
+def test_linear_emits_layernorm_statistics_of_its_output(ops, M, K, N, res):
+    """ccedit_gemm_desc.stats_out: the epilogue's per-row partial (sum, sum of squares) + ccedit_layernorm_stats_combine
+    equal the LayerNorm statistics of the GEMM's output (staged and direct epilogues, with and without residual)."""
+    a, w = rnd(M, K, seed=81), rnd(N, K, seed=82, scale=1 / math.sqrt(K))
+    b = (rnd(N, seed=83).float() + 0.5)
+    r = rnd(M, N, seed=84).cuda() if res else None
+    pw = ops.pack_weight(w.float(), b, "cuda")
+    sp = torch.empty(M, ops.stats_slots(pw), 2, dtype=torch.float32, device="cuda")
+    out = ops.gemm(a.cuda(), pw, torch.empty(M, N, dtype=torch.float16, device="cuda"), res1=r, stats_out=sp)
+    st = ops.layernorm_stats_combine(sp, N)
+    y = out.float().cpu()
+    close(st[:, 0], y.mean(1), "mean from the producing epilogue", rtol=1e-3, atol=1e-3)
+    close(st[:, 1], (y.var(1, unbiased=False) + 1e-5).rsqrt(), "rstd from the producing epilogue", rtol=2e-3, atol=1e-3)
+    close(st, ops.layernorm_stats(out), "vs. the statistics pass", rtol=2e-3, atol=1e-3)
+
+
 @pytest.mark.parametrize("Fr,H,W", [(2, 32, 128), (1, 40, 70), (3, 16, 64), (1, 5, 9)])
 def test_hint_stem_first_two_layers_fused(ops, Fr, H, W):
     """controlmodel.py:215-219: conv3x3(3->16)+SiLU+conv3x3(16->16)+SiLU in one kernel (csrc/hint_stem.cu), ragged tiles."""
@@ -216,6 +234,18 @@ def test_groupnorm_spatial(ops, Fr, HW, C, eps, silu):
     if silu:
         ref = F.silu(ref)
     close(out, ref.permute(0, 2, 1), f"GN spatial C={C}")
+
+
+def test_groupnorm_spatial_scratch_is_shape_independent(ops):
+    """The single-pass kernel's arrival counters live at a fixed place of the per-stream scratch: launches with different
+    frame counts / sizes back to back must not see each other's partial sums as counters (regression)."""
+    for Fr, HW, C in [(34, 384, 320), (2, 1536, 640), (5, 96, 1280), (34, 96, 320), (1, 6144, 320), (3, 200, 64)]:
+        x = rnd(Fr, HW, C, seed=Fr + HW) + 0.25
+        gamma, beta = rnd(C, seed=16).float(), rnd(C, seed=17).float()
+        for _ in range(2):
+            y = ops.groupnorm_spatial(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5, True)
+        ref = F.silu(F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+        close(y, ref, f"GN spatial {Fr}x{HW}x{C}")
 
 
 @pytest.mark.parametrize("B,T,HW,C,silu", [(2, 17, 40, 320, True), (1, 3, 24, 1280, False), (2, 33, 10, 640, True),
