@@ -35,6 +35,7 @@
 namespace ccedit {
 extern std::atomic<long long> g_launch_count;
 extern long long* g_trace_buf;
+int device_sm_count();
 
 constexpr int kTcTile = 128;                 // query rows per tile
 constexpr int kTcDefaultEmu = 1;             // exponentials per group of 4 evaluated on the FMA pipe
@@ -50,6 +51,7 @@ struct FaTcParams {
   int ntile[2];
   int lq, d;
   float scale_log2;
+  int hpc;            // heads per CTA (> 1 for short key sequences: amortises the CTA set-up, overlaps the next Q load)
   long long* trace;   // diagnostics (ccedit_gemm_trace): per-tile phase clocks of CTA 0, or nullptr
 };
 
@@ -179,7 +181,7 @@ struct T2Cfg {
   static_assert(ColO + NO <= 256, "TMEM budget");
 };
 
-template <int KSTEPS, int EMU>
+template <int KSTEPS, int EMU, bool MH>   // MH: several heads per CTA (p.hpc), for short key sequences
 __global__ void __launch_bounds__(kT2Threads, 2)
 flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                       const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
@@ -205,9 +207,11 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   float* lsum = smax + 512;                              // [128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTcTile, head = blockIdx.y, f = blockIdx.z;
+  const int hpc = MH ? p.hpc : 1;
+  const int q0 = blockIdx.x * kTcTile, head0 = blockIdx.y * hpc, f = blockIdx.z;
   const int d = p.d;
-  const int ntiles = p.ntile[0] + p.ntile[1];
+  const int ntiles = p.ntile[0] + p.ntile[1];     // key tiles per head
+  const int total = ntiles * hpc;                 // (head, key tile) items of this CTA, heads outermost
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmK0);
@@ -236,7 +240,9 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int j = 0; j < ntiles; ++j) {
+    for (int it = 0; it < total; ++it) {
+      const int hl = MH ? it / ntiles : 0, j = it - hl * ntiles;
+      const int head = head0 + hl;
       const int seg = j < p.ntile[0] ? 0 : 1;
       const int k0 = (seg == 0 ? j : j - p.ntile[0]) * KT;
       const int kvf = (f / p.kv_div[seg]) * p.kv_mul[seg] + p.kv_add[seg];
@@ -274,16 +280,23 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     }
     int stage = 0;
     uint32_t phase = 0;
-    for (int j = 0; j < ntiles; ++j) {
+    for (int it = 0; it < total; ++it) {
+      const int hl = MH ? it / ntiles : 0, j = it - hl * ntiles;
+      const bool last_tile = j + 1 == ntiles;
       int nstage = stage + 1;
       uint32_t nphase = phase;
       if (nstage == kT2Stages) {
         nstage = 0;
         nphase ^= 1u;
       }
-      if (j + 1 < ntiles) {                              // next scores: S is free once it sits in registers
+      auto next_scores = [&]() {                         // S(it+1) = Q K^T: S is free once it sits in registers
+        if (it + 1 >= total) return;
         mbar_wait(&kv_full[nstage], nphase);
-        mbar_wait(s_free, static_cast<uint32_t>(j & 1));
+        mbar_wait(s_free, static_cast<uint32_t>(it & 1));
+        if (MH && last_tile) {                           // first key tile of the next head: its Q tile must have landed
+          mbar_wait(q_full, static_cast<uint32_t>((hl + 1) & 1));
+          fence_proxy_async_smem();
+        }
         tcgen05_fence_after();
         const uint32_t sKa = smem_u32(sKV + nstage * 2 * Cfg::KBytes);
 #pragma unroll
@@ -291,15 +304,19 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa + (ks >> 2) * (kTcTile * 128)) + 2u * (ks & 3),
                            umma_desc_k_sw128(sKa + (ks >> 2) * (KT * 128)) + 2u * (ks & 3), idesc_s, ks ? 1u : 0u);
         umma_commit_warp(s_full);
-      }
+      };
+      // within a head the next scores go first (they are ready long before P); across heads P.V goes first, because the
+      // next head's Q tile is published only after this tile's softmax
+      if (!(MH && last_tile)) next_scores();
       // V tile: MN-major, 64-channel atoms KT * 128 bytes apart (LBO), 16 keys (2 KiB) per k-step
       const uint64_t dV = umma_desc_mn_sw128(smem_u32(sKV + stage * 2 * Cfg::KBytes + Cfg::KBytes), KT * 128);
-      mbar_wait(p_full, static_cast<uint32_t>(j & 1));
+      mbar_wait(p_full, static_cast<uint32_t>(it & 1));
       tcgen05_fence_after();
 #pragma unroll
       for (int kk = 0; kk < KT / 16; ++kk)
-        umma_f16_ts_warp(tO, ((kPx && kk < 2 && (j & 1)) ? tPx : tP) + 8u * kk, dV + 128u * kk, idesc_o, (j | kk) ? 1u : 0u);
+        umma_f16_ts_warp(tO, ((kPx && kk < 2 && (it & 1)) ? tPx : tP) + 8u * kk, dV + 128u * kk, idesc_o, (j | kk) ? 1u : 0u);
       umma_commit_warp(o_done);
+      if (MH && last_tile) next_scores();
       umma_commit_warp(&kv_empty[stage]);
       stage = nstage;
       phase = nphase;
@@ -309,8 +326,11 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     const int half = (warp - 2) >> 2;
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
-    if (half == 0) {
-      // ---- Q tile load: thread copies query row `row` (zero-filled beyond lq and in the padded channels) ----
+    // ---- Q tile load (half 0): thread copies query row `row` of head h (zero-filled beyond lq and in the padded channels).
+    // The first head's tile is waited for right away; the next head's tile is requested while the last key tile of the
+    // current head is still being processed (its QK^T has completed by then, so the buffer is free) and waited for at
+    // the end of the head. ----
+    auto q_issue = [&](int head) {
       const int chunks = d >> 3;
       const int qrow = q0 + row;
       const bool ok = qrow < p.lq;
@@ -323,9 +343,15 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       for (int c = chunks; c < 2 * KSTEPS; ++c)
         *reinterpret_cast<uint4*>(dst + (c >> 3) * (kTcTile * 128) + (((c & 7) ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
       cp_async_commit();
+    };
+    auto q_publish = [&]() {
       cp_async_wait<0>();
       fence_proxy_async_smem();
       mbar_arrive(q_full);
+    };
+    if (half == 0) {
+      q_issue(head0);
+      q_publish();
     }
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t tS = tmem_base + lane_off + Cfg::ColS + static_cast<uint32_t>(HK * half);
@@ -334,10 +360,48 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     const uint32_t tPx = tmem_base + lane_off + Cfg::ColX;
     const float c = p.scale_log2;
     float mref = -INFINITY, l = 0.f;
-    for (int j = 0; j < ntiles; ++j) {
+    // ---- end of a head: merge the row sums; O / l -> fp16 -> global, the 16-column chunks split between the halves ----
+    auto head_epilogue = [&](int it, int head, float l) {
+      lsum[half * 128 + row] = l;
+      named_bar_sync(1, 256);
+      const float lt = l + lsum[(half ^ 1) * 128 + row];
+      mbar_wait(o_done, static_cast<uint32_t>(it & 1));
+      tcgen05_fence_after();
+      const int qrow = q0 + row;
+      const float inv = 1.f / lt;
+      __half* dst = p.o + static_cast<long long>(f) * p.o_fs + static_cast<long long>(qrow < p.lq ? qrow : 0) * p.ldo +
+                    static_cast<long long>(head) * d;
+#pragma unroll 1
+      for (int cc = 16 * half; cc < NO; cc += 32) {
+        uint32_t o[16];
+        tmem_ld_x16(tO + cc, o);
+        tmem_ld_wait();
+        if (qrow < p.lq) {
+#pragma unroll
+          for (int h8 = 0; h8 < 16; h8 += 8) {
+            if (cc + h8 < d) {
+              uint4 u;
+              u.x = pack_h2(__uint_as_float(o[h8]) * inv, __uint_as_float(o[h8 + 1]) * inv);
+              u.y = pack_h2(__uint_as_float(o[h8 + 2]) * inv, __uint_as_float(o[h8 + 3]) * inv);
+              u.z = pack_h2(__uint_as_float(o[h8 + 4]) * inv, __uint_as_float(o[h8 + 5]) * inv);
+              u.w = pack_h2(__uint_as_float(o[h8 + 6]) * inv, __uint_as_float(o[h8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + cc + h8) = u;
+            }
+          }
+        }
+      }
+    };
+    for (int it = 0; it < total; ++it) {
+      const int hl = MH ? it / ntiles : 0, j = it - hl * ntiles;   // head (local), key tile
+      const int head = head0 + hl;
+      const bool last_tile = j + 1 == ntiles;
+      if (MH && j == 0) {
+        mref = -INFINITY;
+        l = 0.f;
+      }
       const int seg = j < p.ntile[0] ? 0 : 1;
       const int valid = p.lkv[seg] - (seg == 0 ? j : j - p.ntile[0]) * KT - HK * half;   // my keys that exist
-      mbar_wait(s_full, static_cast<uint32_t>(j & 1));
+      mbar_wait(s_full, static_cast<uint32_t>(it & 1));
       tcgen05_fence_after();
       uint32_t r[HK];
 #pragma unroll
@@ -345,6 +409,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(s_free);
+      if (MH && half == 0 && last_tile && hl + 1 < hpc) q_issue(head + 1);   // Q of the next head (this head's QK^T are done)
       if (valid < HK) {
 #pragma unroll
         for (int i = 0; i < HK; ++i)
@@ -359,7 +424,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         m3 = max3_f(m3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
       }
       const float mloc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      float* sm = smax + (j & 1) * 256 + row;
+      float* sm = smax + (it & 1) * 256 + row;
       sm[half * 128] = mloc;
       named_bar_sync(1, 256);                             // both halves of every row have published their maximum
       const float mt = fmaxf(mloc, sm[(half ^ 1) * 128]) * c;
@@ -369,9 +434,9 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         alpha = ex2_approx(mref - mt);
         mref = mt;
       }
-      bool owait = j > 0;                                // P / O still belong to P.V of the previous tile
+      bool owait = it > 0;                               // P / O still belong to P.V of the previous tile
       if (j > 0 && __any_sync(0xffffffffu, need)) {       // rare after the first tiles; the 16-column chunks alternate
-        mbar_wait(o_done, static_cast<uint32_t>((j - 1) & 1));
+        mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
         tcgen05_fence_after();
         owait = false;
 #pragma unroll 1
@@ -407,46 +472,24 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         }
         const bool alt = kPx && half == 0 && cc == 0;     // the first 32 keys of P have a second buffer (odd tiles)
         if (owait && !alt) {
-          mbar_wait(o_done, static_cast<uint32_t>((j - 1) & 1));
+          mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
           tcgen05_fence_after();
           owait = false;
         }
-        tmem_st_x16(((alt && (j & 1)) ? tPx : tP) + (cc >> 1), pk);
+        tmem_st_x16(((alt && (it & 1)) ? tPx : tP) + (cc >> 1), pk);
       }
       l += (s0 + s1) + (s2 + s3);
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(p_full);
-    }
-    // ---- epilogue: merge the row sums; O / l -> fp16 -> global, the 16-column chunks split between the halves ----
-    lsum[half * 128 + row] = l;
-    named_bar_sync(1, 256);
-    l += lsum[(half ^ 1) * 128 + row];
-    mbar_wait(o_done, static_cast<uint32_t>((ntiles - 1) & 1));
-    tcgen05_fence_after();
-    const int qrow = q0 + row;
-    const float inv = 1.f / l;
-    __half* dst = p.o + static_cast<long long>(f) * p.o_fs + static_cast<long long>(qrow < p.lq ? qrow : 0) * p.ldo +
-                  static_cast<long long>(head) * d;
-#pragma unroll 1
-    for (int cc = 16 * half; cc < NO; cc += 32) {
-      uint32_t o[16];
-      tmem_ld_x16(tO + cc, o);
-      tmem_ld_wait();
-      if (qrow < p.lq) {
-#pragma unroll
-        for (int h8 = 0; h8 < 16; h8 += 8) {
-          if (cc + h8 < d) {
-            uint4 u;
-            u.x = pack_h2(__uint_as_float(o[h8]) * inv, __uint_as_float(o[h8 + 1]) * inv);
-            u.y = pack_h2(__uint_as_float(o[h8 + 2]) * inv, __uint_as_float(o[h8 + 3]) * inv);
-            u.z = pack_h2(__uint_as_float(o[h8 + 4]) * inv, __uint_as_float(o[h8 + 5]) * inv);
-            u.w = pack_h2(__uint_as_float(o[h8 + 6]) * inv, __uint_as_float(o[h8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + cc + h8) = u;
-          }
-        }
+      if (MH && last_tile) {
+        if (half == 0 && hl + 1 < hpc) q_publish();        // before the epilogue: the MMA warp needs it for the next QK^T
+        head_epilogue(it, head, l);
+        tcgen05_fence_before();                            // O has been read before the next head's first P.V overwrites it
+        named_bar_sync(1, 256);                            // lsum / smax are free for the next head
       }
     }
+    if (!MH) head_epilogue(total - 1, head0, l);
   }
 
   tcgen05_fence_before();
@@ -490,23 +533,29 @@ static bool make_kv_map(CUtensorMap* m, const void* base, int cols, int rows, lo
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int KSTEPS, int EMU>
-static int launch_tc2(const CUtensorMap* maps, const FaTcParams& p, int frames, int heads, cudaStream_t st) {
+template <int KSTEPS, int EMU, bool MH>
+static int launch_tc2_t(const CUtensorMap* maps, const FaTcParams& p, int frames, int heads, cudaStream_t st) {
   const int smem = T2Cfg<KSTEPS>::Smem;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(flash_attn_tc2_kernel<KSTEPS, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_err = cudaFuncSetAttribute(flash_attn_tc2_kernel<KSTEPS, EMU, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   if (attr_err != cudaSuccess) {
     set_last_error("ccedit_attention(tc2): cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
     return CCEDIT_ERR_CUDA;
   }
-  dim3 grid((p.lq + kTcTile - 1) / kTcTile, heads, frames);
-  flash_attn_tc2_kernel<KSTEPS, EMU><<<grid, kT2Threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  dim3 grid((p.lq + kTcTile - 1) / kTcTile, heads / p.hpc, frames);
+  flash_attn_tc2_kernel<KSTEPS, EMU, MH><<<grid, kT2Threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_attention(tc2)");
   return CCEDIT_OK;
+}
+
+template <int KSTEPS, int EMU>
+static int launch_tc2(const CUtensorMap* maps, const FaTcParams& p, int frames, int heads, cudaStream_t st) {
+  return p.hpc > 1 ? launch_tc2_t<KSTEPS, EMU, true>(maps, p, frames, heads, st)
+                   : launch_tc2_t<KSTEPS, EMU, false>(maps, p, frames, heads, st);
 }
 
 // Returns -1 when the problem is not eligible for the tcgen05 kernel (caller falls back to the mma.sync kernel),
@@ -552,6 +601,23 @@ int attention_tc(const ccedit_attn_desc* a, cudaStream_t st) {
   p.d = a->d;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.trace = g_trace_buf;
+  // Heads per CTA: with one or two key tiles per head (text cross-attention: 77 keys) a CTA's life is all set-up
+  // (TMEM allocation, barrier init, descriptor fetch, Q / K / V latency: ~6 us for ~1.5 us of work), so it takes several
+  // heads in a row as long as enough CTAs remain to fill the 2 x 148 slots a few times over.
+  p.hpc = 1;
+  {
+    static const int force = [] { const char* e = getenv("CCEDIT_ATTN_HPC"); return e ? atoi(e) : 0; }();
+    const int sms = device_sm_count();
+    const long long items = static_cast<long long>((a->lq + kTcTile - 1) / kTcTile) * a->frames;
+    if (p.ntile[0] + p.ntile[1] <= 2 && sms > 0) {
+      for (int h = 8; h >= 2; h >>= 1)
+        if (a->heads % h == 0 && items * (a->heads / h) >= 3ll * 2 * sms) {
+          p.hpc = h;
+          break;
+        }
+    }
+    if (force > 0 && a->heads % force == 0) p.hpc = force;
+  }
   static const int emu = [] {                      // developer switch (A/B of the FMA-pipe exponentials at d = 40)
     const char* e = getenv("CCEDIT_ATTN_EMU");
     return e ? atoi(e) : kTcDefaultEmu;

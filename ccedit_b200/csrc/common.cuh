@@ -108,7 +108,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a pipeline bug must not hang the GPU (a hung box is a lost lease); trap instead.
 #ifndef CCEDIT_MBAR_SPIN_LIMIT
-#define CCEDIT_MBAR_SPIN_LIMIT (1u << 26)
+#define CCEDIT_MBAR_SPIN_LIMIT (1u << 21)   // >= 0.2 s of polling; no legitimate wait outlives its kernel (ms)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;

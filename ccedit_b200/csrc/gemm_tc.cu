@@ -951,7 +951,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     }
     ok = ok && (!p.res1 || (reinterpret_cast<uintptr_t>(p.res1) & 15) == 0);
     const int W = ncols_out / 2;
-    const int cb = W == 128 ? 64 : W;
+    const int cb = W % 64 == 0 ? 64 : (W == 96 ? 32 : W);    // TMA-swizzled 128 / 64-byte staging rows where rows would collide
     ok = ok && (cb <= 128) && (W % cb == 0);
     if (ok) {
       const int tbuf = kBlockM * ncols_out * 2;

@@ -75,12 +75,19 @@ def _require(t: torch.Tensor, dtype=torch.float16, name="tensor"):
 # weights
 # ---------------------------------------------------------------------------------------------------------------------
 def pick_bn(n: int, geglu: bool = False, max_bn: int = 256) -> int:
-    """Largest N tile (multiple of 16, <= max_bn <= 256; multiple of 32 for GEGLU) that divides n."""
+    """N tile (multiple of 16, <= max_bn <= 256; multiple of 32 for GEGLU) that divides n: the largest one, unless a tile
+    at least 3/4 as wide has an even number of 16-column chunks - the staged (TMA-store) epilogue of the tap-GEMM splits
+    the tile's columns between two warpgroups (e.g. n = 960: 192 instead of 240)."""
     step = 32 if geglu else 16
-    for bn in range(max_bn - max_bn % step, 0, -step):
-        if n % bn == 0:
-            return bn
-    raise ValueError(f"output width {n} is not a multiple of {step}")
+    cands = [bn for bn in range(max_bn - max_bn % step, 0, -step) if n % bn == 0]
+    if not cands:
+        raise ValueError(f"output width {n} is not a multiple of {step}")
+    best = cands[0]
+    if not geglu and best % 32 != 0:
+        for bn in cands[1:]:
+            if bn % 32 == 0 and 4 * bn >= 3 * best:
+                return bn
+    return best
 
 
 @dataclass

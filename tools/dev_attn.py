@@ -47,6 +47,24 @@ def bench(Fr, L, heads, d, iters=5, scale=1.0):
     print(f"attn F={Fr} L={L} d={d} scale={scale}: {ms:8.3f} ms  {4.0 * Fr * L * L * C / ms / 1e9:8.1f} TFLOP/s", flush=True)
 
 
+def bench_cross(Fr, L, Lkv, heads, d, iters=10):
+    C = heads * d
+    q = torch.randn(Fr, L, C, device=dev).half()
+    kv = torch.randn(2, Lkv, 2 * C, device=dev).half()
+    out = torch.empty(Fr, L, C, dtype=torch.float16, device=dev)
+    run = lambda: ops.attention(q, [ops.KVSegment(kv[..., :C], kv[..., C:], div=Fr // 2)], heads, out)
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"cross-attn F={Fr} L={L} Lkv={Lkv} d={d}: {ms * 1e3:8.1f} us  {2.0 * Fr * L * C * 2 / ms / 1e6:7.0f} GB/s (q + o)", flush=True)
+
+
 def trace():
     from ccedit_b200 import _lib
     buf = torch.zeros(64, 16, dtype=torch.int64, device=dev)
@@ -88,3 +106,6 @@ if __name__ == "__main__":
     bench(34, 1536, 8, 40)
     bench(34, 1536, 8, 80)
     bench(34, 384, 8, 160)
+    bench_cross(34, 6144, 77, 8, 40)
+    bench_cross(34, 1536, 77, 8, 80)
+    bench_cross(34, 384, 77, 8, 160)
