@@ -272,25 +272,29 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
   v += col0;
   o += col0;
   const int RS = C + 8;                                   // smem row stride (halves)
-  __half* sq = reinterpret_cast<__half*>(ta_smem);        // [TK][RS]
-  __half* sk = sq + TK * RS;
-  __half* sv = sk + TK * RS;
+  // Only the T real frames are staged ([T][RS] per tensor): fragment rows T..TK-1 alias frame T-1 - padded keys are
+  // masked to -inf before the softmax (so their P is exactly 0 and any finite V row will do) and padded query rows are
+  // never stored.  At T = 17 this halves the shared memory of a CTA (3 x 17 instead of 3 x 32 rows) and doubles the CTAs
+  // per SM, which is what hides the HBM latency of this kernel.
+  __half* sq = reinterpret_cast<__half*>(ta_smem);        // [T][RS]
+  __half* sk = sq + T * RS;
+  __half* sv = sk + T * RS;
+  const int tl = T - 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long pix = blockIdx.x;                       // b*HW + hw
   const int b = static_cast<int>(pix / HW), hw = static_cast<int>(pix % HW);
   const long long row0 = (static_cast<long long>(b) * T) * HW + hw;  // row of frame 0; frame t adds t*HW
   const int cpr = C >> 3;                                 // 16-byte chunks per row
-  for (int i = threadIdx.x; i < TK * cpr; i += blockDim.x) {
+  for (int i = threadIdx.x; i < T * cpr; i += blockDim.x) {
     const int t = i / cpr, c = i - t * cpr;
-    const bool ok = t < T;
-    const long long row = row0 + static_cast<long long>(ok ? t : 0) * HW;
-    cp_async_16(smem_u32(sq + t * RS + c * 8), q + row * ldq + c * 8, ok);
-    cp_async_16(smem_u32(sk + t * RS + c * 8), k + row * ldk + c * 8, ok);
-    cp_async_16(smem_u32(sv + t * RS + c * 8), v + row * ldv + c * 8, ok);
+    const long long row = row0 + static_cast<long long>(t) * HW;
+    cp_async_16(smem_u32(sq + t * RS + c * 8), q + row * ldq + c * 8, true);
+    cp_async_16(smem_u32(sk + t * RS + c * 8), k + row * ldk + c * 8, true);
+    cp_async_16(smem_u32(sv + t * RS + c * 8), v + row * ldv + c * 8, true);
   }
   // the 8 padding halves at the end of every row feed the last k-step of the last head: keep them finite
-  for (int i = threadIdx.x; i < 3 * TK; i += blockDim.x)
+  for (int i = threadIdx.x; i < 3 * T; i += blockDim.x)
     *reinterpret_cast<uint4*>(sq + i * RS + C) = make_uint4(0, 0, 0, 0);
   cp_async_commit();
   cp_async_wait<0>();
@@ -310,12 +314,12 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
       for (int ks = 0; ks < KSTEPS; ++ks) {
         if (ks * 16 >= d) break;                                   // DP may exceed d by whole k-steps (e.g. d = 96)
         uint32_t qf[4];
-        ldmatrix_x4(qf, smem_u32(hq + (m0 + (lane & 15)) * RS + ks * 16 + (lane >> 4) * 8));
+        ldmatrix_x4(qf, smem_u32(hq + min(m0 + (lane & 15), tl) * RS + ks * 16 + (lane >> 4) * 8));
         if (mask_tail && d - ks * 16 == 8) qf[2] = qf[3] = 0u;     // zero the 8 channels past d
 #pragma unroll
         for (int np = 0; np < NTK / 2; ++np) {
           uint32_t kf[4];
-          ldmatrix_x4(kf, smem_u32(hk + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * RS + ks * 16 + ((lane >> 3) & 1) * 8));
+          ldmatrix_x4(kf, smem_u32(hk + min(np * 16 + (lane & 7) + ((lane >> 4) << 3), tl) * RS + ks * 16 + ((lane >> 3) & 1) * 8));
           const uint32_t b0[2] = {kf[0], kf[1]}, b1[2] = {kf[2], kf[3]};
           mma_m16n8k16(sacc[2 * np], qf, b0);
           mma_m16n8k16(sacc[2 * np + 1], qf, b1);
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
         for (int np = 0; np < NT_O / 2; ++np) {
           if (np * 16 >= d) break;                                 // DP may exceed d by whole 16-column groups
           uint32_t vf[4];
-          ldmatrix_x4_trans(vf, smem_u32(hv + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * RS + np * 16 + (lane >> 4) * 8));
+          ldmatrix_x4_trans(vf, smem_u32(hv + min(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, tl) * RS + np * 16 + (lane >> 4) * 8));
           const uint32_t b0[2] = {vf[0], vf[1]}, b1[2] = {vf[2], vf[3]};
           mma_m16n8k16(oacc[2 * np], pf[kk], b0);
           mma_m16n8k16(oacc[2 * np + 1], pf[kk], b1);
@@ -373,8 +377,11 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
       }
       const float inv0 = 1.f / rs[0], inv1 = 1.f / rs[1];
       const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
-      __half* o0 = o + (row0 + static_cast<long long>(r0) * HW) * ldo + head * d;
-      __half* o1 = o + (row0 + static_cast<long long>(r1) * HW) * ldo + head * d;
+      // the output rows of this head replace its query rows in shared memory (they are not needed any more: Q of block m0
+      // only feeds S of block m0); the CTA writes whole [T][C] rows to global memory afterwards, 16 bytes per thread
+      __half* o0 = sq + r0 * RS + head * d;
+      __half* o1 = sq + r1 * RS + head * d;
+      __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < NT_O; ++nt) {
         const int col = nt * 8 + (lane & 3) * 2;
@@ -385,14 +392,20 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
       }
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * cpr; i += blockDim.x) {
+    const int t = i / cpr, c = i - t * cpr;
+    *reinterpret_cast<uint4*>(o + (row0 + static_cast<long long>(t) * HW) * ldo + c * 8) =
+        *reinterpret_cast<const uint4*>(sq + t * RS + c * 8);
+  }
 }
 
 template <int DP, int TK>
 static int launch_ta(const __half* q, long long ldq, const __half* k, long long ldk, const __half* v, long long ldv, __half* o,
                      long long ldo, int B, int T, int HW, int heads, int d, float scale_log2, cudaStream_t st) {
   int hpb = heads;   // heads per CTA: all of them unless the pixel's q/k/v rows do not fit in shared memory
-  auto smem_for = [&](int h) { return static_cast<size_t>(3) * TK * (h * d + 8) * 2; };
-  while (hpb > 1 && (smem_for(hpb) > 200 * 1024 || heads % hpb != 0)) --hpb;
+  auto smem_for = [&](int h) { return static_cast<size_t>(3) * T * (h * d + 8) * 2; };
+  while (hpb > 1 && (smem_for(hpb) > 72 * 1024 || heads % hpb != 0)) --hpb;   // <= 72 KB: three CTAs per SM
   const size_t smem = smem_for(hpb);
   CCEDIT_CHECK_ARG(smem <= 227 * 1024, "ccedit_temporal_attention: T*d too large for shared memory (%zu bytes)", smem);
   static bool attr_done = false;
