@@ -47,6 +47,8 @@ class GemmDesc(C.Structure):
         ("rowstats", C.c_void_p),
         ("colsum", C.c_void_p),
         ("stats_out", C.c_void_p),
+        ("rowstats_slots", C.c_int32),
+        ("ln_eps", C.c_float),
     ]
 
 

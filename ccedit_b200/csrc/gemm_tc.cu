@@ -68,6 +68,8 @@ struct GemmKParams {
   // LayerNorm folded into the epilogue (template flag LNF): out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]
   const float2* rowstats;
   const float* colsum;
+  int rs_slots;       // > 1: rowstats holds rs_slots (sum, sum of squares) partials per row (another GEMM's stats_out)
+  float rs_invc, rs_eps;
   // Row statistics of THIS GEMM's output for the LayerNorm that follows it: per row and per (n-tile, column half) the
   // epilogue thread writes (sum, sum of squares) of its final fp32 values to stats_out[(m * 2 * n_tiles + slot)].
   float2* stats_out;
@@ -201,9 +203,21 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
     float rstd = 1.f, nmr = 0.f;                              // LNF: 1/std and -mean/std of this thread's row
     if (LNF) {
       const int m = min(dig[1] * p.box[0] + l[0], p.odim[0] - 1);
-      const float2 st = __ldg(p.rowstats + m);
-      rstd = st.y;
-      nmr = -st.x * st.y;
+      if (p.rs_slots > 1) {                                   // partial sums from the producing GEMM's epilogue
+        float ss = 0.f, qq = 0.f;
+        for (int k = 0; k < p.rs_slots; ++k) {
+          const float2 pv = __ldg(p.rowstats + static_cast<long long>(m) * p.rs_slots + k);
+          ss += pv.x;
+          qq += pv.y;
+        }
+        const float mean = ss * p.rs_invc;
+        rstd = rsqrtf(fmaxf(fmaf(-mean, mean, qq * p.rs_invc), 0.f) + p.rs_eps);
+        nmr = -mean * rstd;
+      } else {
+        const float2 st = __ldg(p.rowstats + m);
+        rstd = st.y;
+        nmr = -st.x * st.y;
+      }
     }
     __half* optr = p.out + off_o + col0_out;
     const __half* r1ptr = p.res1 + off_r1 + col0_out;   // dereferenced only if NRES >= 1 and valid
@@ -436,9 +450,21 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
     float rstd = 1.f, nmr = 0.f;                              // LNF: 1/std and -mean/std of this thread's row
     if (LNF) {
       const int m = min(dig[1] * p.box[0] + l[0], p.odim[0] - 1);
-      const float2 st = __ldg(p.rowstats + m);
-      rstd = st.y;
-      nmr = -st.x * st.y;
+      if (p.rs_slots > 1) {                                   // partial sums from the producing GEMM's epilogue
+        float ss = 0.f, qq = 0.f;
+        for (int k = 0; k < p.rs_slots; ++k) {
+          const float2 pv = __ldg(p.rowstats + static_cast<long long>(m) * p.rs_slots + k);
+          ss += pv.x;
+          qq += pv.y;
+        }
+        const float mean = ss * p.rs_invc;
+        rstd = rsqrtf(fmaxf(fmaf(-mean, mean, qq * p.rs_invc), 0.f) + p.rs_eps);
+        nmr = -mean * rstd;
+      } else {
+        const float2 st = __ldg(p.rowstats + m);
+        rstd = st.y;
+        nmr = -st.x * st.y;
+      }
     }
     const __half* r2ptr = p.res2 + off_r2 + col0_out;        // dereferenced only if NRES >= 2 and valid
     // next tile (mixed-radix add with carry)
@@ -1017,6 +1043,10 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     CCEDIT_CHECK_ARG((reinterpret_cast<uintptr_t>(d->rowstats) & 7) == 0, "ccedit_gemm: rowstats must be 8-byte aligned");
     p.rowstats = reinterpret_cast<const float2*>(d->rowstats);
     p.colsum = d->colsum;
+    CCEDIT_CHECK_ARG(d->rowstats_slots >= 0 && d->rowstats_slots <= 64, "ccedit_gemm: rowstats_slots=%d", d->rowstats_slots);
+    p.rs_slots = d->rowstats_slots;
+    p.rs_invc = 1.f / static_cast<float>(d->a_dims[0]);
+    p.rs_eps = d->ln_eps;
     err = geglu ? launch_gemm<kModeGeglu, 0, true>(tm, p, staged, grid, smem_bytes, stream)
                 : launch_gemm<kModePlain, 0, true>(tm, p, staged, grid, smem_bytes, stream);
   } else if (geglu) err = launch_gemm<kModeGeglu, 0>(tm, p, staged, grid, smem_bytes, stream);

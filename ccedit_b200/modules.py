@@ -204,22 +204,20 @@ class BasicTransformerBlock(nn.Module):
         # The three LayerNorms are folded into the GEMMs they feed.  Their row statistics come from the epilogue of the
         # GEMM that produced x (proj_in, attn1.to_out, attn2.to_out) - no pass over the activation at all - or, when the
         # caller has none, from one statistics pass (ops.layernorm_stats).
-        st = ops.layernorm_stats(x) if sp is None else ops.layernorm_stats_combine(sp, C)
+        st = ops.layernorm_stats(x) if sp is None else sp      # partial sums are finished by the consuming epilogue
         qkv = ops.gemm(x, self.attn1.fused(dev, "qkv", ln=self.norm1), _new(x, M, 3 * C), rowstats=st)
         q3 = qkv.view(F, L, 3 * C)
         att = ops.attention(q3[..., :C], [KVSegment(q3[..., C:2 * C], q3[..., 2 * C:])], heads, _new(x, F, L, C))
         o1 = self.attn1.to_out["0"].packed(dev)
         sp = torch.empty(M, ops.stats_slots(o1), 2, dtype=torch.float32, device=dev)
         x = ops.gemm(att.view(M, C), o1, _new(x, M, C), res1=x, stats_out=sp)
-        ops.layernorm_stats_combine(sp, C, out=st)
-        q = ops.gemm(x, self.attn2.to_q.packed_ln(dev, self.norm2), _new(x, M, C), rowstats=st)
+        q = ops.gemm(x, self.attn2.to_q.packed_ln(dev, self.norm2), _new(x, M, C), rowstats=sp)
         k, v = ctx.text_kv[id(self.attn2)]
         att = ops.attention(q.view(F, L, C), [KVSegment(k, v, div=ctx.T)], heads, att)
         o2 = self.attn2.to_out["0"].packed(dev)
         sp2 = sp if ops.stats_slots(o2) == sp.shape[1] else torch.empty(M, ops.stats_slots(o2), 2, dtype=torch.float32, device=dev)
         x = ops.gemm(att.view(M, C), o2, _new(x, M, C), res1=x, stats_out=sp2)
-        ops.layernorm_stats_combine(sp2, C, out=st)
-        return self.ff.run(x, self.norm3, st)
+        return self.ff.run(x, self.norm3, sp2)
 
 
 class BasicTransformerSingleLayerBlock(nn.Module):
@@ -235,15 +233,14 @@ class BasicTransformerSingleLayerBlock(nn.Module):
         """x: tokens [M, C]; attend(q [M,C], kv [M,2C]) -> [M, C] runs the attention of the calling layer; sp: statistics
         partials of x from the GEMM that produced it (see BasicTransformerBlock.run)."""
         dev, C, M = x.device, x.shape[1], x.shape[0]
-        st = ops.layernorm_stats(x) if sp is None else ops.layernorm_stats_combine(sp, C)
+        st = ops.layernorm_stats(x) if sp is None else sp      # partial sums are finished by the consuming epilogue
         q = ops.gemm(x, self.attn1.to_q.packed_ln(dev, self.norm1), _new(x, M, C), rowstats=st)
         kv = ops.gemm(x, self.attn1.fused(dev, "kv"), _new(x, M, 2 * C))
         att = attend(q, kv)
         o1 = self.attn1.to_out["0"].packed(dev)
         sp = torch.empty(M, ops.stats_slots(o1), 2, dtype=torch.float32, device=dev)
         x = ops.gemm(att, o1, _new(x, M, C), res1=x, stats_out=sp)
-        ops.layernorm_stats_combine(sp, C, out=st)
-        return self.ff.run(x, self.norm2, st, out)
+        return self.ff.run(x, self.norm2, sp, out)
 
 
 class SpatialTransformer(nn.Module):

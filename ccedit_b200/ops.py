@@ -226,7 +226,7 @@ def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = 
          rowbias: Optional[torch.Tensor] = None, rb_dim: int = 0, rb_div: int = 1,
          res1: Optional[torch.Tensor] = None, res2: Optional[torch.Tensor] = None, silu: bool = False,
          box: Optional[tuple] = None, rowstats: Optional[torch.Tensor] = None,
-         stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         stats_out: Optional[torch.Tensor] = None, ln_eps: float = 1e-5) -> torch.Tensor:
     """out[p, :] = epi( sum_tap A[p + tap, :] @ W[:, tap, :]^T ).  a/out/res*: [d4, d3, d2, d1, C] views (C contiguous)."""
     _require(a, name="a")
     _require(out, name="out")
@@ -283,10 +283,13 @@ def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = 
         raise RuntimeError("ccedit_b200.gemm: rowstats go with a LayerNorm-folded weight (pack_weight(ln_gamma=...)) and vice versa")
     if rowstats is not None:
         _require(rowstats, torch.float32, "rowstats")
-        if rowstats.shape != (odims[0], 2) or not rowstats.is_contiguous():
-            raise RuntimeError(f"ccedit_b200.gemm: rowstats must be contiguous [{odims[0]}, 2]")
+        if not rowstats.is_contiguous() or rowstats.shape[0] != odims[0] or rowstats.shape[-1] != 2 or rowstats.dim() not in (2, 3):
+            raise RuntimeError(f"ccedit_b200.gemm: rowstats must be contiguous [{odims[0]}, 2] (mean, rstd) or "
+                               f"[{odims[0]}, P, 2] partial sums from gemm(stats_out=)")
         d.rowstats = rowstats.data_ptr()
         d.colsum = pw.colsum.data_ptr()
+        d.rowstats_slots = rowstats.shape[1] if rowstats.dim() == 3 else 0
+        d.ln_eps = ln_eps
     if stats_out is not None:
         _require(stats_out, torch.float32, "stats_out")
         if tuple(stats_out.shape) != (odims[0], stats_slots(pw), 2) or not stats_out.is_contiguous():

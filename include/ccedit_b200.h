@@ -91,6 +91,10 @@ typedef struct ccedit_gemm_desc {
    * the final fp32 values of its row over its column range.  ccedit_layernorm_stats_combine turns them into (mean, rstd).
    * Plain 2-D GEMMs only (no GEGLU / SiLU).  NULL => off. */
   float* stats_out;
+  /* rowstats_slots > 1: rowstats is not (mean, rstd) but the [M][rowstats_slots][2] partial sums another GEMM wrote
+   * through stats_out; the epilogue finishes them itself with eps = ln_eps over a_dims[0] channels (no combine kernel). */
+  int32_t rowstats_slots;
+  float ln_eps;
 } ccedit_gemm_desc;
 
 int ccedit_gemm(const ccedit_gemm_desc* d, void* stream);

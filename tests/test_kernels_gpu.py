@@ -167,6 +167,13 @@ def test_linear_emits_layernorm_statistics_of_its_output(ops, M, K, N, res):
     close(st[:, 0], y.mean(1), "mean from the producing epilogue", rtol=1e-3, atol=1e-3)
     close(st[:, 1], (y.var(1, unbiased=False) + 1e-5).rsqrt(), "rstd from the producing epilogue", rtol=2e-3, atol=1e-3)
     close(st, ops.layernorm_stats(out), "vs. the statistics pass", rtol=2e-3, atol=1e-3)
+    # the consuming GEMM can finish the partial sums itself (rowstats = [M, P, 2]): same result as with combined statistics
+    w2 = rnd(320, N, seed=85, scale=1 / math.sqrt(N))
+    gamma, beta = 1 + 0.3 * rnd(N, seed=86).float(), 0.2 * rnd(N, seed=87).float()
+    pw2 = ops.pack_weight(w2.float(), None, "cuda", ln_gamma=gamma, ln_beta=beta)
+    y1 = ops.gemm(out, pw2, torch.empty(M, 320, dtype=torch.float16, device="cuda"), rowstats=st)
+    y2 = ops.gemm(out, pw2, torch.empty(M, 320, dtype=torch.float16, device="cuda"), rowstats=sp)
+    close(y2, y1.float().cpu(), "partial statistics finished in the consuming epilogue", rtol=2e-3, atol=2e-3)
 
 
 @pytest.mark.parametrize("Fr,H,W", [(2, 32, 128), (1, 40, 70), (3, 16, 64), (1, 5, 9)])
