@@ -131,6 +131,47 @@ def test_pick_box_and_bn():
     assert ops.pick_bn(16) == 16 and ops.pick_bn(96) == 96
 
 
+def test_pick_bn_prefers_tiles_the_staged_epilogue_can_split():
+    """An even number of 16-column chunks lets the TMA-store epilogue split the tile between its two warpgroups."""
+    assert ops.pick_bn(960) == 192 and ops.pick_bn(1920) == 192 and ops.pick_bn(640) == 160 and ops.pick_bn(3840) == 256
+    assert ops.pick_bn(336) == 112       # no even-chunk tile within 3/4 of the largest divisor: keep the largest
+
+
+def test_pack_weight_with_folded_layernorm():
+    """attention.py:667-669 feeding a Linear: LN(x) W^T + b == rstd * (x (gamma o W)^T - mean * colsum) + (b + W beta),
+    with colsum taken over the fp16-rounded weight so that the mean term cancels exactly (host-side algebra only)."""
+    g = torch.Generator().manual_seed(5)
+    K, N, M = 64, 48, 37
+    w, b = torch.randn(N, K, generator=g) / 8, torch.randn(N, generator=g)
+    gamma, beta = 1 + 0.3 * torch.randn(K, generator=g), 0.2 * torch.randn(K, generator=g)
+    pw = ops.pack_weight(w, b, "cpu", ln_gamma=gamma, ln_beta=beta)
+    Wp = pw.w.float()[:, :K]
+    assert torch.equal(Wp, (w * gamma[None, :]).half().float())
+    assert torch.allclose(pw.colsum, Wp.sum(1), atol=1e-6) and torch.allclose(pw.bias, b + w @ beta, atol=1e-6)
+    x = (torch.randn(M, K, generator=g) * 1.5 + 4.0).half().float()
+    mean, rstd = x.mean(1, keepdim=True), (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    folded = rstd * (x @ Wp.t() - mean * pw.colsum[None, :]) + pw.bias[None, :]
+    ref = F.linear(F.layer_norm(x, (K,), gamma, beta), w, b)
+    assert rel_err(folded, ref) < 2e-3   # only the fp16 rounding of gamma o W separates the two
+    with pytest.raises(ValueError):
+        ops.pack_weight(torch.randn(8, 8, 3, 3), None, "cpu", ln_gamma=torch.ones(8), ln_beta=torch.zeros(8))
+
+
+def test_pack_hint_stem_weight_layout():
+    """csrc/hint_stem.cu operand layout: [16][kpad] with k = tap * cin_pad + channel, tap = kh * 3 + kw, zero padded."""
+    g = torch.Generator().manual_seed(6)
+    w, b = torch.randn(16, 3, 3, 3, generator=g), torch.randn(16, generator=g)
+    wp, bp = ops.pack_hint_stem_weight(w, b, "cpu", 8, 80)
+    assert wp.shape == (16, 80) and wp.dtype == torch.float16 and torch.equal(bp, b)
+    W = wp.float().view(16, 10, 8)
+    for kh in range(3):
+        for kw in range(3):
+            assert torch.equal(W[:, kh * 3 + kw, :3], w[:, :, kh, kw].half().float())
+    assert float(W[:, :9, 3:].abs().max()) == 0 and float(W[:, 9].abs().max()) == 0
+    with pytest.raises(RuntimeError):
+        ops.pack_hint_stem_weight(torch.randn(32, 3, 3, 3), torch.randn(32), "cpu", 8, 80)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def test_sampler_callers_match_oracle():
     """ccedit_b200.sampling (DiscreteDenoiser / VanillaCFGTV2V / DPMPP2SAncestralSampler) vs the oracle's restatement,
