@@ -184,6 +184,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
   uint32_t aphase = 0;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
   int titer = 0;
+  int staged_ntile = -1;                // N tile whose bias row (and column sums) sit in sbias / scs
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     if (tracing && titer < 64) p.trace[16 * titer + 0] = clock64();
     const int n_tile = dig[0];
@@ -236,20 +237,26 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
         rb_uniform = __all_sync(0xffffffffu, rb_row == __shfl_sync(0xffffffffu, rb_row, 0));
         if (!rb_uniform && valid) rbptr = p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out;
       }
-      float bv[8];
+      // the staged row only depends on the N tile (and on the time-embedding row): a CTA whose tiles all share their N
+      // tile - n_tiles divides the grid, e.g. every N = 320 / 640 GEMM - stages it once (it cost 400-1000 clocks per tile)
+      if (n_tile != staged_ntile || p.rowbias) {
+        staged_ntile = n_tile;
+        __syncwarp();
+        float bv[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {                      // bn <= 256: all loads in flight together
-        const int i = lane + 32 * k;
-        bv[k] = (p.bias && i < p.bn) ? __ldg(p.bias + n_tile * p.bn + i) : 0.f;
-        if (rb_uniform && i < p.bn) bv[k] += __ldg(p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out + i);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sbias[lane + 32 * k] = bv[k];
-      if (LNF) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 8; ++k) {                      // bn <= 256: all loads in flight together
           const int i = lane + 32 * k;
-          scs[i] = i < p.bn ? __ldg(p.colsum + n_tile * p.bn + i) : 0.f;
+          bv[k] = (p.bias && i < p.bn) ? __ldg(p.bias + n_tile * p.bn + i) : 0.f;
+          if (rb_uniform && i < p.bn) bv[k] += __ldg(p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out + i);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sbias[lane + 32 * k] = bv[k];
+        if (LNF) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = lane + 32 * k;
+            scs[i] = i < p.bn ? __ldg(p.colsum + n_tile * p.bn + i) : 0.f;
+          }
         }
       }
     }
@@ -430,6 +437,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
   __syncwarp();
 
   int as = 0, it = 0;
+  int staged_ntile = -1;                // N tile whose bias row (and column sums) sit in sbias / scs
   uint32_t aphase = 0, rph0 = 0, rph1 = 0;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -492,23 +500,27 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
         rb_uniform = __all_sync(0xffffffffu, rb_row == __shfl_sync(0xffffffffu, rb_row, 0));
         if (!rb_uniform && valid) rbptr = p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out;
       }
-      const int nb = GEGLU ? 2 * W : W;
-      float bv[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = lane + 32 * k;
-        const int src = n_tile * p.bn + (GEGLU ? (i < W ? eg * W + i : ncols_out + eg * W + (i - W)) : eg * W + i);
-        bv[k] = (p.bias && i < nb) ? __ldg(p.bias + src) : 0.f;
-        if (rb_uniform && i < nb) bv[k] += __ldg(p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out + i);
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sbias[lane + 32 * k] = bv[k];
-      if (LNF) {
+      if (n_tile != staged_ntile || p.rowbias) {          // see epilogue_loop: once per N tile, not once per tile
+        staged_ntile = n_tile;
+        __syncwarp();
+        const int nb = GEGLU ? 2 * W : W;
+        float bv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int i = lane + 32 * k;
           const int src = n_tile * p.bn + (GEGLU ? (i < W ? eg * W + i : ncols_out + eg * W + (i - W)) : eg * W + i);
-          scs[i] = i < nb ? __ldg(p.colsum + src) : 0.f;
+          bv[k] = (p.bias && i < nb) ? __ldg(p.bias + src) : 0.f;
+          if (rb_uniform && i < nb) bv[k] += __ldg(p.rowbias + static_cast<long long>(rb_row) * p.n_out_total + col0_out + i);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sbias[lane + 32 * k] = bv[k];
+        if (LNF) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = lane + 32 * k;
+            const int src = n_tile * p.bn + (GEGLU ? (i < W ? eg * W + i : ncols_out + eg * W + (i - W)) : eg * W + i);
+            scs[i] = i < nb ? __ldg(p.colsum + src) : 0.f;
+          }
         }
       }
     }
@@ -1025,6 +1037,8 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     set_last_error("ccedit_gemm: no CUDA device");
     return CCEDIT_ERR_CUDA;
   }
+  // (A grid rounded down to a multiple of n_tiles would keep every CTA on one N tile and save the per-tile staging for
+  //  N = 960 / 2560 as well; measured: the SMs given up cost more than the staging - GEGLU 367 -> 391 us.)
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (d->stats_out) {
     CCEDIT_CHECK_ARG(!geglu && !(d->flags & CCEDIT_GEMM_SILU) && d->out_dims[1] == 1 && d->out_dims[2] == 1 && d->out_dims[3] == 1,
