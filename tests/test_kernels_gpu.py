@@ -305,6 +305,19 @@ def test_attention_text_keys_shared_by_frames(ops):
     close(out, ref, "text attention", atol=ATOL_ATTN)
 
 
+@pytest.mark.parametrize("B,T,L,heads,d", [(2, 17, 6144, 8, 40), (2, 17, 1536, 8, 80), (2, 9, 2000, 8, 40)])
+def test_attention_text_keys_many_heads_per_cta(ops, B, T, L, heads, d):
+    """Text cross-attention at the sizes of the network call: with one or two key tiles per head and enough query tiles
+    the kernel takes several heads per CTA in a row (flash_attn_tc2_kernel<.., MH = true>: next-head Q prefetch, per-head
+    statistics reset, O re-initialised by the first P.V) - 8 heads per CTA at L0, 2 at L1."""
+    C = heads * d
+    q, k, v = rnd(B * T, L, C, seed=57), rnd(B, 77, C, seed=58), rnd(B, 77, C, seed=59)
+    out = torch.empty(B * T, L, C, dtype=torch.float16, device="cuda")
+    ops.attention(q.cuda(), [ops.KVSegment(k.cuda(), v.cuda(), div=T)], heads, out)
+    ref = _sdpa(q, k.repeat_interleave(T, 0), v.repeat_interleave(T, 0), heads)
+    close(out, ref, f"text attention, several heads per CTA (L={L}, d={d})", atol=ATOL_ATTN)
+
+
 def test_attention_center_self_two_segments(ops):
     """cfca: K/V = cat([centre-frame tokens (repeated over t), own tokens]) (attention.py:1323-1336)."""
     B, T, L, heads, d = 2, 3, 70, 8, 40
