@@ -39,7 +39,6 @@ int device_sm_count();
 
 constexpr int kTcTile = 128;                 // query rows per tile
 constexpr int kTcDefaultEmu = 1;             // exponentials per group of 4 evaluated on the FMA pipe
-constexpr int kTcTileBytes = 128 * 128;      // [128 rows][64 halves], SWIZZLE_128B
 
 struct FaTcParams {
   const __half* q;

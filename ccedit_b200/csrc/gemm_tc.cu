@@ -32,7 +32,6 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr int kGemmThreads = 320;
 constexpr int kEpiWarps = 8;                 // two epilogue warpgroups
-constexpr int kMaxChunks = 8;                // 16-column chunks per thread: 256 output columns / 16 / 2 groups
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;              // columns between the two accumulator buffers
 

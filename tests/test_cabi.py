@@ -76,5 +76,7 @@ def test_sass_uses_blackwell_tensor_and_tma_paths(lib_path):
     """The GEMM kernel is tcgen05 + TMA: UTC*MMA / LDTM / UTMALDG must appear in the sm_100a SASS."""
     out = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
     assert "sm_100a" in out or "SM100a" in out.replace("_", "") or "arch = sm_100" in out
-    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+    # tcgen05.mma / tcgen05.ld / tcgen05.st (P of the attention kernel lives in TMEM) / TMA load (2-D weights, 3-D K/V,
+    # 5-D activations) / TMA store (staged GEMM epilogue)
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG.2D", "UTMALDG.3D", "UTMALDG.5D", "UTMASTG.5D"):
         assert mnemonic in out, f"{mnemonic} missing from SASS"
