@@ -181,6 +181,9 @@ __global__ void gn_spatial_apply_kernel(const __half* __restrict__ x, __half* __
 // version above reads the tensor twice from HBM at the big levels (134 MB per activation > L2 once all frames are in
 // flight); here the second read is an L2 hit for most of the slice.  Statistics stay deterministic (fixed-order sums).
 // counters: [F][2] ints, zero before the first launch; the last CTA to leave a frame's barrier resets them.
+// Co-residency: the host sizes the grid at 80 % of the occupancy limit and the path launches on ONE stream, so no other
+// kernel competes for the SMs; if that assumption is ever broken the bounded spin traps (launch failure, no hang), and
+// CCEDIT_GN_FUSED=0 selects the two-kernel version.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void gn_spatial_fused_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
