@@ -84,7 +84,7 @@ SIGNATURES = {
     "ccedit_attention": (C.c_int, [C.POINTER(AttnDesc), _vp]),
     "ccedit_temporal_attention": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32,
                                             _f32, _vp]),
-    "ccedit_ncthw_to_cl": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp]),
+    "ccedit_ncthw_to_cl": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp]),
     "ccedit_out_temporal": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ccedit_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
     "ccedit_linear_small": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -200,7 +200,9 @@ class UNetModel(nn.Module):
                 m._emb_pack = m._kv_pack = None
 
     def _param_version(self, holders):
-        return tuple((h.weight._version, h.weight.data_ptr()) for h in holders)
+        """Version key over EVERY tensor a fused pack caches (weights and biases)."""
+        return tuple((h.weight._version, h.weight.data_ptr()) + (() if h.bias is None else (h.bias._version, h.bias.data_ptr()))
+                     for h in holders)
 
     def _prepare_ctx(self, timesteps: torch.Tensor, context: Optional[torch.Tensor], B: int, T: int, dev) -> Ctx:
         """Everything that depends only on (t, text): time embedding MLP (openaimodel.py:1216-1223), the SiLU+Linear of
@@ -212,7 +214,7 @@ class UNetModel(nn.Module):
         mods = self._own_modules()
         resblocks = [m for m in mods if isinstance(m, ResBlock)]
         holders = [r.emb_layers["1"] for r in resblocks]
-        ver = (dev, self._param_version(holders))
+        ver = (dev, self._param_version(holders + [self.time_embed["0"], self.time_embed["2"]]))
         if self._emb_pack is None or self._emb_pack[0] != ver:
             w = torch.cat([h.weight.detach().float() for h in holders], 0).to(device=dev, dtype=torch.float16).contiguous()
             b = torch.cat([h.bias.detach().float() for h in holders], 0).to(device=dev).contiguous()

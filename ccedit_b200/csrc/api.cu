@@ -23,5 +23,5 @@ void set_last_error(const char* fmt, ...) {
 }  // namespace ccedit
 
 extern "C" const char* ccedit_last_error(void) { return ccedit::g_err; }
-extern "C" int ccedit_abi_version(void) { return 2; }
+extern "C" int ccedit_abi_version(void) { return 3; }
 extern "C" int64_t ccedit_launch_count(void) { return ccedit::g_launch_count.load(); }

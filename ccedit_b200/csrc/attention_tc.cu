@@ -35,7 +35,6 @@
 namespace ccedit {
 extern std::atomic<long long> g_launch_count;
 extern long long* g_trace_buf;
-int device_sm_count();
 
 constexpr int kTcTile = 128;                 // query rows per tile
 constexpr int kTcDefaultEmu = 1;             // exponentials per group of 4 evaluated on the FMA pipe
@@ -535,14 +534,16 @@ static bool make_kv_map(CUtensorMap* m, const void* base, int cols, int rows, lo
 template <int KSTEPS, int EMU, bool MH>
 static int launch_tc2_t(const CUtensorMap* maps, const FaTcParams& p, int frames, int heads, cudaStream_t st) {
   const int smem = T2Cfg<KSTEPS>::Smem;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(flash_attn_tc2_kernel<KSTEPS, EMU, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  });
-  if (attr_err != cudaSuccess) {
-    set_last_error("ccedit_attention(tc2): cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    return CCEDIT_ERR_CUDA;
+  static std::atomic<bool> attr_set[kMaxDevices];
+  const int dev = current_device();
+  CCEDIT_CHECK_ARG(dev >= 0, "ccedit_attention(tc2): no current CUDA device");
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(flash_attn_tc2_kernel<KSTEPS, EMU, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_last_error("ccedit_attention(tc2): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CCEDIT_ERR_CUDA;
+    }
+    attr_set[dev].store(true, std::memory_order_release);
   }
   dim3 grid((p.lq + kTcTile - 1) / kTcTile, heads / p.hpc, frames);
   flash_attn_tc2_kernel<KSTEPS, EMU, MH><<<grid, kT2Threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);

@@ -35,6 +35,10 @@ void set_last_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
+constexpr int kMaxDevices = 64;   // per-device caches (function attributes, SM counts) are arrays of this size
+int current_device();             // cudaGetDevice() ordinal, -1 if unavailable / out of range
+int device_sm_count();
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // small utilities

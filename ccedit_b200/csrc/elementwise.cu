@@ -10,7 +10,7 @@ extern std::atomic<long long> g_launch_count;
 // [B][Cin][T][H][W] -> [B][T][H][W][Cpad] fp16, v*mul+add, zero padded channels. One thread per pixel.
 template <typename SrcT>
 __global__ void ncthw_to_cl_kernel(const SrcT* __restrict__ src, __half* __restrict__ dst, int Cin, int T, long long HW,
-                                   int Cpad, float mul, float add, long long total) {
+                                   int Cpad, float pre, float mul, float add, long long total) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // over B*T*HW
   if (i >= total) return;
   const long long hw = i % HW;
@@ -24,7 +24,7 @@ __global__ void ncthw_to_cl_kernel(const SrcT* __restrict__ src, __half* __restr
     for (int j = 0; j < 8; ++j) {
       const int c = c0 + j;
       float v = 0.f;
-      if (c < Cin) v = static_cast<float>(src[((b * Cin + c) * T + t) * HW + hw]) * mul + add;
+      if (c < Cin) v = __fmaf_rn(__fadd_rn(static_cast<float>(src[((b * Cin + c) * T + t) * HW + hw]), pre), mul, add);
       h[j] = __float2half_rn(v);
     }
     *reinterpret_cast<uint4*>(d + c0) = *reinterpret_cast<const uint4*>(h);
@@ -215,7 +215,7 @@ static inline unsigned blocks_for(long long total, int threads) {
 using namespace ccedit;
 
 extern "C" int ccedit_ncthw_to_cl(const void* src, int32_t src_f32, void* dst, int32_t B, int32_t Cin, int32_t T,
-                                  int32_t H, int32_t W, int32_t Cpad, float mul, float add, void* stream) {
+                                  int32_t H, int32_t W, int32_t Cpad, float pre, float mul, float add, void* stream) {
   CCEDIT_CHECK_ARG(src && dst, "ccedit_ncthw_to_cl: null pointer");
   CCEDIT_CHECK_ARG(B > 0 && Cin > 0 && T > 0 && H > 0 && W > 0 && Cpad >= Cin && Cpad % 8 == 0,
                    "ccedit_ncthw_to_cl: bad shape B=%d Cin=%d T=%d H=%d W=%d Cpad=%d", B, Cin, T, H, W, Cpad);
@@ -223,12 +223,12 @@ extern "C" int ccedit_ncthw_to_cl(const void* src, int32_t src_f32, void* dst, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src_f32)
     ncthw_to_cl_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const float*>(src),
-                                                                      static_cast<__half*>(dst), Cin, T, HW, Cpad, mul,
-                                                                      add, total);
+                                                                      static_cast<__half*>(dst), Cin, T, HW, Cpad, pre,
+                                                                      mul, add, total);
   else
     ncthw_to_cl_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(src),
-                                                                       static_cast<__half*>(dst), Cin, T, HW, Cpad, mul,
-                                                                       add, total);
+                                                                       static_cast<__half*>(dst), Cin, T, HW, Cpad, pre,
+                                                                       mul, add, total);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_ncthw_to_cl");
   return CCEDIT_OK;

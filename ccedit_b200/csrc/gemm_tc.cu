@@ -819,14 +819,21 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// Per-device caches: function attributes and SM counts belong to a device, and one process may drive several.
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices ? dev : -1;
+}
 int device_sm_count() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = -1;
+  static std::atomic<int> sms[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return -1;
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    sms[dev].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
 }
 
 extern long long* g_trace_buf;
@@ -834,13 +841,15 @@ extern long long* g_trace_buf;
 template <int MODE, int NRES, bool STAGED, bool LNF>
 static cudaError_t launch_gemm_t(const CUtensorMap* tm, const GemmKParams& p, int grid, int smem_bytes,
                                  cudaStream_t stream) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tap_gemm_kernel<MODE, NRES, STAGED, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return attr_err;
+  static std::atomic<bool> attr_set[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return cudaErrorInvalidDevice;
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<MODE, NRES, STAGED, LNF>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev].store(true, std::memory_order_release);
+  }
   tap_gemm_kernel<MODE, NRES, STAGED, LNF><<<grid, kGemmThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   return cudaGetLastError();
 }
@@ -963,7 +972,8 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.res1 = static_cast<const __half*>(d->res1);
   p.res2 = static_cast<const __half*>(d->res2);
   p.flags = d->flags;
-  { const char* e = getenv("CCEDIT_GEMM_DEV"); if (e) p.flags |= atoi(e) << 8; }   // developer experiments only
+  static const int dev_flags = [] { const char* e = getenv("CCEDIT_GEMM_DEV"); return e ? atoi(e) << 8 : 0; }();
+  p.flags |= dev_flags;                                                           // developer experiments only
   p.idesc = umma_idesc_f16(kBlockM, d->bn);
   p.trace = g_trace_buf;
   const int stage_bytes = kABytes + d->bn * kBlockK * 2;
@@ -980,8 +990,9 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   bool staged = false;
   {
     const int ncols_out = geglu ? d->bn / 2 : d->bn;
-    const char* force = getenv("CCEDIT_GEMM_EPI");       // developer switch: 0 = always direct, 1 = staged wherever legal
-    bool ok = ncols_out % 32 == 0 && (!force || atoi(force) != 0);
+    // developer switch: 0 = always direct, 1 = staged wherever legal (read once per process)
+    static const int force_epi = [] { const char* e = getenv("CCEDIT_GEMM_EPI"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    bool ok = ncols_out % 32 == 0 && force_epi != 0;
     for (int i = 0; i < 4 && ok; ++i) {
       ok = d->out_strides[i] % 8 == 0 && (!p.res1 || p.r1[i] % 8 == 0);
       // a size-1 grid axis may carry any stride; TMA still wants it 16-byte aligned
@@ -993,7 +1004,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     if (ok) {
       const int tbuf = kBlockM * ncols_out * 2;
       // the K loop hides a direct epilogue of ~5-8k clocks once a tile has >= ~5k clocks of MMAs (measured: K = 1280, BN = 160 is faster direct)
-      const bool wanted = (force && atoi(force) != 0) || kblocks * d->bn <= 15 * 160;
+      const bool wanted = force_epi == 1 || kblocks * d->bn <= 15 * 160;
       int nbuf = nres >= 1 ? 2 : 1;
       int st = (budget - nbuf * tbuf) / stage_bytes;
       if (st < 3 && nbuf == 2) {

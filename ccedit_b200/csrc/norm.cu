@@ -181,9 +181,10 @@ __global__ void gn_spatial_apply_kernel(const __half* __restrict__ x, __half* __
 // version above reads the tensor twice from HBM at the big levels (134 MB per activation > L2 once all frames are in
 // flight); here the second read is an L2 hit for most of the slice.  Statistics stay deterministic (fixed-order sums).
 // counters: [F][2] ints, zero before the first launch; the last CTA to leave a frame's barrier resets them.
-// Co-residency: the host sizes the grid at 80 % of the occupancy limit and the path launches on ONE stream, so no other
-// kernel competes for the SMs; if that assumption is ever broken the bounded spin traps (launch failure, no hang), and
-// CCEDIT_GN_FUSED=0 selects the two-kernel version.
+// Co-residency is GUARANTEED, not assumed: the kernel is launched cooperatively (cudaLaunchAttributeCooperative), so
+// the driver schedules the grid only when every CTA can be resident at once - whatever else runs on the device (other
+// streams, NCCL kernels, MPS neighbours) - and refuses the launch (-> two-kernel version) if the grid cannot fit at all.
+// The bounded spin remains as a last line of defence.  CCEDIT_GN_FUSED=0 selects the two-kernel version.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void gn_spatial_fused_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                         const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -532,19 +533,35 @@ extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gam
     static const bool disabled = [] { const char* e = getenv("CCEDIT_GN_FUSED"); return e && atoi(e) == 0; }();
     if (!disabled && sms > 0 &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_spatial_fused_kernel, threads, smem) == cudaSuccess) {
-      const long long capacity = static_cast<long long>(per_sm) * sms * 4 / 5;   // margin: the barrier needs co-residency
+      const long long capacity = static_cast<long long>(per_sm) * sms * 4 / 5;   // margin below the cooperative-launch limit
       int nsplit = static_cast<int>(capacity / F);
       const int want = static_cast<int>(bytes / 16384) > 0 ? static_cast<int>(bytes / 16384) : 1;   // >= 16 KB per slice
       if (nsplit > want) nsplit = want;
       if (nsplit > kMaxSplit) nsplit = kMaxSplit;
       if (nsplit >= 1 && 2 * F <= kGnCounterFloats) {
         int* counters = reinterpret_cast<int*>(partial);      // fixed place: [kGnCounterFloats] ints ahead of the partial sums
-        gn_spatial_fused_kernel<<<dim3(nsplit, F), threads, smem, st>>>(
-            static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, partial + kGnCounterFloats, counters, HW, C,
-            nvec, rpi, eps, silu);
-        g_launch_count.fetch_add(1, std::memory_order_relaxed);
-        CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_spatial(fused)");
-        return CCEDIT_OK;
+        const __half* xa = static_cast<const __half*>(x);
+        __half* ya = static_cast<__half*>(y);
+        float* pa = partial + kGnCounterFloats;
+        void* args[] = {&xa, &ya, &gamma, &beta, &pa, &counters, &HW, &C, const_cast<int*>(&nvec), const_cast<int*>(&rpi),
+                        &eps, &silu};
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(nsplit, F);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeCooperative;
+        attr.val.cooperative = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        const cudaError_t le = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(gn_spatial_fused_kernel), args);
+        if (le == cudaSuccess) {
+          g_launch_count.fetch_add(1, std::memory_order_relaxed);
+          return CCEDIT_OK;
+        }
+        (void)cudaGetLastError();                              // grid refused (too large for co-residency): two-kernel version
       }
     }
   }

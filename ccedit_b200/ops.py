@@ -41,15 +41,19 @@ def profile_start() -> None:
     _PROF = []
 
 
-def profile_stop():
-    """-> list of (kernel class, flops, bytes, milliseconds); synchronises the device."""
+def profile_stop(executed: bool = False):
+    """-> list of (kernel class, flops, bytes, milliseconds[, executed flops]); synchronises the device.
+    flops = useful FLOPs of the launch; executed flops include what the tensor cores spend on padding (K padded to 64,
+    head dim padded to a multiple of 16, partial row / key tiles)."""
     global _PROF
     recs, _PROF = _PROF or [], None
     torch.cuda.synchronize()
-    return [(name, fl, by, e0.elapsed_time(e1)) for name, fl, by, e0, e1 in recs]
+    if executed:
+        return [(name, fl, by, e0.elapsed_time(e1), xf) for name, fl, by, e0, e1, xf in recs]
+    return [(name, fl, by, e0.elapsed_time(e1)) for name, fl, by, e0, e1, _ in recs]
 
 
-def _call(name: str, fn, args, flops: float = 0.0, nbytes: float = 0.0) -> None:
+def _call(name: str, fn, args, flops: float = 0.0, nbytes: float = 0.0, xflops: Optional[float] = None) -> None:
     if _PROF is None:
         _lib.check(fn(*args), name)
         return
@@ -57,7 +61,11 @@ def _call(name: str, fn, args, flops: float = 0.0, nbytes: float = 0.0) -> None:
     e0.record()
     _lib.check(fn(*args), name)
     e1.record()
-    _PROF.append((name, flops, nbytes, e0, e1))
+    _PROF.append((name, flops, nbytes, e0, e1, flops if xflops is None else xflops))
+
+
+def _ceil_to(x: int, m: int) -> int:
+    return -(-x // m) * m
 
 
 def _nb(*ts) -> int:
@@ -301,8 +309,9 @@ def gemm(a: torch.Tensor, pw: PackedWeight, out: torch.Tensor, taps: Sequence = 
         kind = "gemm.linear_geglu"
     if _PROF_SHAPES:
         kind += f"[M={m_rows},K={pw.ntaps}x{min(c, pw.k)},N={pw.n},bn={pw.bn},res={int(res1 is not None) + int(res2 is not None)}]"
+    m_exec = math.prod(-(-o // b) * b for o, b in zip(odims, bx))
     _call(kind, _lib.load().ccedit_gemm, (C.byref(d), _stream()), flops=2.0 * m_rows * pw.ntaps * min(c, pw.k) * pw.n,
-          nbytes=_nb(a, pw.w, out, res1, res2))
+          nbytes=_nb(a, pw.w, out, res1, res2), xflops=2.0 * m_exec * pw.ntaps * pw.kpad * pw.n)
     return out
 
 
@@ -445,7 +454,8 @@ def attention(q: torch.Tensor, segments: Sequence[KVSegment], heads: int, out: t
     kvb = sum(2.0 * seg.k.shape[0] * seg.k.shape[1] * Cc * 2 for seg in segments)   # each K/V row read once (ideal)
     _call("attention" + (f"[F={F},L={L},Lkv={lkv},d={dh}]" if _PROF_SHAPES else ""), _lib.load().ccedit_attention,
           (C.byref(a), _stream()), flops=4.0 * F * L * lkv * Cc,
-          nbytes=2.0 * F * L * Cc * 2 + kvb)
+          nbytes=2.0 * F * L * Cc * 2 + kvb, xflops=4.0 * F * _ceil_to(L, 128) * heads * _ceil_to(dh, 16) *
+          sum(_ceil_to(seg.k.shape[1], 128 if dh <= 64 else 64) for seg in segments))
     return out
 
 
@@ -459,15 +469,16 @@ def temporal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads:
     sc = float(dh) ** -0.5 if scale is None else scale
     _call("temporal_attention", _lib.load().ccedit_temporal_attention,
           (q.data_ptr(), q.stride(2), k.data_ptr(), k.stride(2), v.data_ptr(), v.stride(2), out.data_ptr(), out.stride(2),
-           B, T, HW, heads, dh, sc, _stream()), flops=4.0 * B * HW * T * T * Cc, nbytes=4.0 * B * T * HW * Cc * 2)
+           B, T, HW, heads, dh, sc, _stream()), flops=4.0 * B * HW * T * T * Cc, nbytes=4.0 * B * T * HW * Cc * 2,
+          xflops=4.0 * B * HW * _ceil_to(T, 16) ** 2 * heads * _ceil_to(dh, 16))
     return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # small kernels
 # ---------------------------------------------------------------------------------------------------------------------
-def ncthw_to_cl(src: torch.Tensor, cpad: int, mul: float = 1.0, add: float = 0.0) -> torch.Tensor:
-    """[B, C, T, H, W] fp32/fp16 -> [B, T, H, W, cpad] fp16 (v*mul+add, zero padded channels)."""
+def ncthw_to_cl(src: torch.Tensor, cpad: int, mul: float = 1.0, add: float = 0.0, pre: float = 0.0) -> torch.Tensor:
+    """[B, C, T, H, W] fp32/fp16 -> [B, T, H, W, cpad] fp16 ((v + pre) * mul + add, zero padded channels)."""
     if not src.is_cuda:
         raise RuntimeError("ccedit_b200: src must be a CUDA tensor (no CPU fallback)")
     if src.dtype not in (torch.float32, torch.float16):
@@ -476,7 +487,7 @@ def ncthw_to_cl(src: torch.Tensor, cpad: int, mul: float = 1.0, add: float = 0.0
     B, Cin, T, H, W = src.shape
     dst = torch.empty(B, T, H, W, cpad, dtype=torch.float16, device=src.device)
     _call("ncthw_to_cl", _lib.load().ccedit_ncthw_to_cl,
-          (src.data_ptr(), int(src.dtype == torch.float32), dst.data_ptr(), B, Cin, T, H, W, cpad, mul, add, _stream()),
+          (src.data_ptr(), int(src.dtype == torch.float32), dst.data_ptr(), B, Cin, T, H, W, cpad, pre, mul, add, _stream()),
           nbytes=_nb(src, dst))
     return dst
 

@@ -46,20 +46,21 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
         B, _, T, h, w = x.shape
         x_cl = _to_cl(x, 8)                                                       # [B, T, h, w, 8]
         # hint: 1 - (hint + 1) / 2  (wrappers.py:160-162) folded into the layout change
-        hint_cl = ops.ncthw_to_cl(control_hint, 8, mul=-0.5, add=0.5)             # [B, T, 8h, 8w, 8]
+        hint_cl = ops.ncthw_to_cl(control_hint, 8, pre=1.0, mul=-0.5, add=1.0)    # [B, T, 8h, 8w, 8]
         control = net.controlnet.forward_cl(x_cl.view(B * T, h, w, 8),
                                             hint_cl.view(B * T, hint_cl.shape[2], hint_cl.shape[3], 8), t, crossattn,
                                             B, T)
         img_control = None
         if cond_feat is not None:
             feat_cl = _to_cl(cond_feat.unsqueeze(2), 8)                           # [B, 1, h, w, 8]
-            img_control = net.controlnet_img.forward_cl(None, feat_cl.view(B, h, w, 8), t, crossattn, B, 1)
+            # wrappers.py:180-186: controlnet_img sees the centre frame of x (ignored when it was built with no_add_x)
+            xc_cl = None if net.controlnet_img.no_add_x else x_cl[:, T // 2].contiguous()
+            img_control = net.controlnet_img.forward_cl(xc_cl, feat_cl.view(B, h, w, 8), t, crossattn, B, 1)
         return net.forward_cl(x_cl, t, crossattn, control, img_control, False, x.dtype)
 
     def _graphed(self, x, t, crossattn, control_hint, cond_feat):
-        ins = dict(x=x, t=t, crossattn=crossattn, control_hint=control_hint)
-        if cond_feat is not None:
-            ins["cond_feat"] = cond_feat
+        ins = dict(x=x, t=t, crossattn=crossattn, control_hint=control_hint, cond_feat=cond_feat)
+        ins = {k: v for k, v in ins.items() if v is not None}
         key = tuple((k, tuple(v.shape), v.dtype, v.device) for k, v in ins.items())
         ent = self._graphs.get(key)
         wver = self._weights_version()
@@ -70,7 +71,7 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
             static = {k: torch.empty_like(v, memory_format=torch.contiguous_format) for k, v in ins.items()}
             for k, v in ins.items():
                 static[k].copy_(v)
-            args = (static["x"], static["t"], static["crossattn"], static["control_hint"], static.get("cond_feat"))
+            args = (static["x"], static["t"], static.get("crossattn"), static["control_hint"], static.get("cond_feat"))
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                # warm-up: packs weights, sets kernel attributes
@@ -105,10 +106,25 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
             return self._network(*args)
 
     def _weights_version(self):
+        """Cheap staleness probe for the captured graphs: the autograd version counters of all parameters (bumped by
+        load_state_dict, `p.add_()`, `state_dict()[k] += ...` - the reference's LoRA merge, sampling_tv2v.py:211-234) plus
+        the storage of the first few.  Edits through `p.data` (`p.data.copy_()`, EMA swaps) do NOT bump the counters:
+        call `invalidate()` after those."""
         if self._params is None:
             self._params = list(self.diffusion_model.parameters())
         return sum(p._version for p in self._params) + sum(p.data_ptr() for p in self._params[:8])
 
     def reset_graphs(self):
-        """Drop captured graphs (after weights change: load_state_dict, LoRA merge)."""
+        """Drop captured graphs (keeps the packed fp16 weights)."""
         self._graphs.clear()
+
+    def invalidate(self):
+        """Call after ANY weight edit the version counters cannot see (`p.data` writes, EMA swaps, re-assigned
+        parameters): drops every packed fp16 kernel copy, the fused embedding / text-K/V packs and the captured CUDA
+        graphs; the next call re-packs and re-captures.  ccedit_b200.checkpoint.merge_lora / load_network_state_dict
+        call it themselves."""
+        self._graphs.clear()
+        self._params = None
+        for m in self.diffusion_model.modules():
+            if hasattr(m, "invalidate_packed"):
+                m.invalidate_packed()

@@ -157,9 +157,11 @@ int ccedit_temporal_attention(const void* q, int64_t ldq, const void* k, int64_t
  * Small / layout kernels.
  * ------------------------------------------------------------------------------------------------------------------ */
 /* [B][Cin][T][H][W] (fp32 if src_f32 else fp16) -> channels-last fp16 [B][T][H][W][Cpad], channels >= Cin zeroed,
- * value = v*mul + add (the hint transform 1-(h+1)/2 of wrappers.py:160-162 is mul=-0.5, add=0.5). */
+ * value = fp16( fma( fl32(v + pre), mul, add ) ).  The hint transform 1 - (h + 1) / 2 of wrappers.py:160-162 is
+ * pre = 1, mul = -0.5, add = 1: the same two fp32 roundings torch makes, so the fused transform is bit-identical to
+ * transforming in PyTorch and converting afterwards. */
 int ccedit_ncthw_to_cl(const void* src, int32_t src_f32, void* dst, int32_t B, int32_t Cin, int32_t T, int32_t H,
-                       int32_t W, int32_t Cpad, float mul, float add, void* stream);
+                       int32_t W, int32_t Cpad, float pre, float mul, float add, void* stream);
 /* UNet tail (controlmodel.py:550; openaimodel.py:1627-1632): y is the spatial out conv result, channels-last fp16
  * [B][T][HW][ldy] (first Cout channels valid); dst[b][c][t][hw] = y + bias_t[c] + sum_{dt,c'} wt[c][c'][dt] *
  * silu(y[b][t+dt-1][hw][c']) with zero padding in t; dst is fp32 if dst_f32 else fp16, layout [B][Cout][T][HW]. */

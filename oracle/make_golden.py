@@ -156,8 +156,61 @@ def run(kind):
             print("sampler done:", len(calls), "network calls", round(time.time() - t0, 1), "s", flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# full-size fixtures: ONE network call of the unmodified reference at the headline shape (BASELINE configs[1] / [2]:
+# CFG batch 2 x 17 keyframes x latent 64x96) and at two corners of the configs[4] sweep, plus the same call through the
+# oracle's fp16-storage emulation (sgm_oracle.emulate_half_storage) - the error floor of any fp16-storage implementation.
+# Inputs and weights are regenerated from seeds by the tests; only the outputs (0.8 MB each) are committed.
+#   python -m oracle.make_golden full tv2v headline sweep33 sweep9        (about 4 min per reference call on 8 cores)
+# ---------------------------------------------------------------------------------------------------------------------
+FULL_CASES = {
+    #  name      (B, T, h, w)      t    cond seed, latent seed
+    "headline": ((1, 17, 64, 96), 500, 31, 32),
+    "sweep33": ((1, 33, 24, 32), 250, 41, 42),
+    "sweep9": ((1, 9, 48, 72), 250, 41, 42),
+}
+
+
+def run_full(kind, names):
+    from oracle import sgm_oracle as so
+    path = os.path.join(GOLDEN_DIR, f"full_{kind}.pt")
+    store = torch.load(path, weights_only=False) if os.path.exists(path) else {}
+    t0 = time.time()
+    wrap = ref_import.build_reference_network(kind)
+    from oracle.weights import load_manifest
+    sd = seeded_state_dict(load_manifest(kind), seed=0)
+    wrap.load_state_dict(sd, strict=True)
+    print(kind, "reference built", round(time.time() - t0, 1), "s", flush=True)
+    ucfg, icfg = so.TV2V_UNET_CFG, None
+    if kind == "tvi2v":
+        ucfg = dict(so.TV2V_UNET_CFG, enable_attention3d_crossframe=True, ST3DCA_ca_type="center_self")
+        icfg = dict(so.TV2V_CONTROLNET_CFG, no_add_x=True, set_input_hint_block_as_identity=True, disable_text_ca=True)
+    for name in names:
+        (B, T, h, w), t, cs, ls = FULL_CASES[name]
+        c, uc = oin.synthetic_cond(B, T, h, w, seed=cs, tvi2v=(kind == "tvi2v"))
+        xin, tin, cc = oin.cfg_batch(oin.synthetic_latent(B, T, h, w, seed=ls), torch.tensor([t]), c, uc)
+        with torch.no_grad():
+            t1 = time.time()
+            ref = wrap(xin, tin, cc)
+            dt_ref = time.time() - t1
+            print(kind, name, "reference call", round(dt_ref, 1), "s", flush=True)
+            t1 = time.time()
+            with so.emulate_half_storage():
+                emu = so.wrapper_forward(sd, ucfg, so.TV2V_CONTROLNET_CFG, xin, tin, cc, icfg)
+            dt_emu = time.time() - t1
+        err = float((emu - ref).abs().max() / ref.abs().max())
+        print(kind, name, "fp16-storage emulation", round(dt_emu, 1), "s; max|emu-ref|/max|ref| =", f"{err:.3e}", flush=True)
+        store[name] = dict(shape=(B, T, h, w), t=t, cond_seed=cs, latent_seed=ls, x_checksum=oin.checksum(xin),
+                           hint_checksum=oin.checksum(cc["control_hint"]), output=ref.clone(), output_half_emulated=emu.clone(),
+                           ref_seconds=dt_ref, threads=torch.get_num_threads())
+        torch.save(store, path)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
-    for kind in (sys.argv[1:] or ["tv2v", "tvi2v"]):
-        run(kind)
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        run_full(sys.argv[2], sys.argv[3:] or list(FULL_CASES))
+    else:
+        for kind in (sys.argv[1:] or ["tv2v", "tvi2v"]):
+            run(kind)

@@ -19,6 +19,7 @@ tests/test_oracle_golden.py checks this file against those fixtures.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional
 
@@ -81,6 +82,31 @@ def unet_plan(cfg) -> dict:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# fp16-storage emulation (test-side only).  The reference runs this path on a GPU under torch.cuda.amp.autocast()
+# (scripts/sampling/sampling_tv2v.py:361-362): conv / linear / SDPA take fp16 operands and return fp16 tensors, the
+# norms and softmax run in fp32.  `with emulate_half_storage():` makes the oracle round exactly those operands and
+# results to fp16 (arithmetic stays fp32 on the CPU, i.e. fp32 accumulation as on tensor cores).  The distance between
+# this variant and the plain fp32 oracle is the error ANY fp16-storage implementation of the path carries; the parity
+# tests compare the CUDA path's own distance with it (tests/test_network_gpu.py, profiles/r02_parity.md).
+# ---------------------------------------------------------------------------------------------------------------------
+_HALF = False
+
+
+@contextlib.contextmanager
+def emulate_half_storage(enabled: bool = True):
+    global _HALF
+    old, _HALF = _HALF, enabled
+    try:
+        yield
+    finally:
+        _HALF = old
+
+
+def _r(t):
+    return t.half().float() if (_HALF and t is not None) else t
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # leaf ops
 # ---------------------------------------------------------------------------------------------------------------------
 def _gn(sd: SD, p: str, x, eps):
@@ -88,15 +114,15 @@ def _gn(sd: SD, p: str, x, eps):
 
 
 def _conv2d(sd: SD, p: str, x, stride=1, padding=1):
-    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding)
+    return _r(F.conv2d(_r(x), _r(sd[p + ".weight"]), sd.get(p + ".bias"), stride=stride, padding=padding))
 
 
 def _conv1d(sd: SD, p: str, x, padding):
-    return F.conv1d(x, sd[p + ".weight"], sd.get(p + ".bias"), padding=padding)
+    return _r(F.conv1d(_r(x), _r(sd[p + ".weight"]), sd.get(p + ".bias"), padding=padding))
 
 
 def _linear(sd: SD, p: str, x):
-    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+    return _r(F.linear(_r(x), _r(sd[p + ".weight"]), sd.get(p + ".bias")))
 
 
 def timestep_embedding(timesteps, dim, max_period=10000):
@@ -138,7 +164,7 @@ def cross_attention(sd: SD, p: str, x, context, heads):
     k = _linear(sd, p + ".to_k", context)
     v = _linear(sd, p + ".to_v", context)
     q, k, v = (rearrange(t, "b n (h d) -> b h n d", h=heads) for t in (q, k, v))
-    out = F.scaled_dot_product_attention(q, k, v)
+    out = _r(F.scaled_dot_product_attention(q, k, v))
     out = rearrange(out, "b h n d -> b n (h d)")
     return _linear(sd, p + ".to_out.0", out)
 

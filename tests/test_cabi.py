@@ -44,7 +44,7 @@ def test_ctypes_mirror_matches_header(lib_path):
     from ccedit_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.ccedit_abi_version() == 2
+    assert lib.ccedit_abi_version() == 3
     assert lib.ccedit_launch_count() >= 0
     # struct sizes agree with the C compiler's layout of the header
     prog = r'''

@@ -345,10 +345,10 @@ def test_temporal_attention(ops, B, T, HW, heads, d):
 
 def test_layout_and_small_kernels(ops):
     x = torch.randn(2, 3, 4, 16, 24, generator=torch.Generator().manual_seed(36))
-    cl = ops.ncthw_to_cl(x.cuda(), 8, mul=-0.5, add=0.5)
+    cl = ops.ncthw_to_cl(x.cuda(), 8, pre=1.0, mul=-0.5, add=1.0)
     ref = torch.zeros(2, 4, 16, 24, 8)
-    ref[..., :3] = (0.5 - 0.5 * x).permute(0, 2, 3, 4, 1)
-    close(cl, ref, "ncthw_to_cl (hint transform)")
+    ref[..., :3] = (1 - (x + 1) / 2.0).permute(0, 2, 3, 4, 1)                      # wrappers.py:160-162, as torch computes it
+    assert torch.equal(cl.cpu(), ref.half()), "fused hint transform must equal transform-in-torch + fp16 conversion bit for bit"
     t = torch.tensor([0.0, 417.0, 999.0])
     from oracle.sgm_oracle import timestep_embedding
     assert_close(ops.timestep_embedding(t.cuda(), 320), timestep_embedding(t, 320), 1e-4, 2e-4, "timestep embedding")

@@ -169,7 +169,7 @@ def check_small():
     report("ncthw_to_cl", y[..., :4], x.permute(0, 2, 3, 4, 1))
     assert y[..., 4:].abs().max().item() == 0
     h = torch.rand(2, 3, 3, 16, 24, device=dev) * 2 - 1
-    report("hint transform", ops.ncthw_to_cl(h, 8, -0.5, 0.5)[..., :3], (1 - (h + 1) / 2).permute(0, 2, 3, 4, 1))
+    report("hint transform", ops.ncthw_to_cl(h, 8, -0.5, 1.0, 1.0)[..., :3], (1 - (h + 1) / 2).permute(0, 2, 3, 4, 1))
     t = torch.tensor([999.0, 17.0, 0.0], device=dev)
     half = 160
     freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=dev) / half)
