@@ -124,14 +124,24 @@ def workload_config(args):
 
 class Workload:
     """One rank's share of a workload: `clips` clips of (kind, T, h, w) run as ONE batch through the sampler step
-    (CFG batch 2 * clips), with pinned host copies of every input for the end-to-end variant."""
+    (CFG batch 2 * clips), with pinned host copies of every input for the end-to-end variant.
 
-    def __init__(self, wrap, dev, kind, clips, T, h, w, sampler_steps, cfg_scale, seed):
-        from ccedit_b200.sampling import DiscreteDenoiser, DPMPP2SAncestralSampler
-        self.wrap, self.dev = wrap, dev
+    fused=True (default): ccedit_b200.sampling.FusedDPMPP2SAncestralSampler - per-step elementwise math in 3 CUDA kernels,
+    the whole step (both network calls) replayed from one CUDA graph, CFG de-duplication of the layers ahead of the
+    first text cross-attention.  fused=False: the PyTorch-elementwise DPMPP2SAncestralSampler.sampler_step with the
+    wrapper's per-call graph (round-1 behaviour)."""
+
+    def __init__(self, wrap, dev, kind, clips, T, h, w, sampler_steps, cfg_scale, seed, fused=True, graph=True, dedup=True):
+        from ccedit_b200.sampling import (BoundDenoiser, DiscreteDenoiser, DPMPP2SAncestralSampler,
+                                          FusedDPMPP2SAncestralSampler)
+        self.wrap, self.dev, self.fused = wrap, dev, fused
         den = DiscreteDenoiser().to(dev)
-        self.sampler = DPMPP2SAncestralSampler(num_steps=sampler_steps, device=dev, eta=1.0, s_noise=1.0, guider_config={
-            "target": "sgm.modules.diffusionmodules.guiders.VanillaCFGTV2V", "params": {"scale": cfg_scale}})
+        gcfg = {"target": "sgm.modules.diffusionmodules.guiders.VanillaCFGTV2V", "params": {"scale": cfg_scale}}
+        if fused:
+            self.sampler = FusedDPMPP2SAncestralSampler(num_steps=sampler_steps, device=dev, eta=1.0, s_noise=1.0,
+                                                        guider_config=gcfg, use_cuda_graph=graph, cfg_dedup=dedup)
+        else:
+            self.sampler = DPMPP2SAncestralSampler(num_steps=sampler_steps, device=dev, eta=1.0, s_noise=1.0, guider_config=gcfg)
         self.sigmas = self.sampler.discretization(sampler_steps, device=dev)
         parts = [synthetic_clip(kind, T, h, w, seed=seed + 1000 * i) for i in range(clips)]
         cat = lambda ts: torch.cat(ts, 0).pin_memory()
@@ -140,13 +150,19 @@ class Workload:
         self.uc_h = {k: cat([p[2][k] for p in parts]) for k in parts[0][2]}
         self.out_h = torch.empty_like(self.x_h).pin_memory()
         self.x_d, self.c_d, self.uc_d = self.x_h.to(dev), self._to_dev(self.c_h), self._to_dev(self.uc_h)
-        self.denoiser = lambda inp, sigma, cond: den(wrap, inp, sigma, cond)
+        self.denoiser = BoundDenoiser(den, wrap)
         self.s_in = torch.ones(clips, device=dev)
         self.n_sched = sampler_steps - 1                 # every step but the last makes 2 network calls
         self.x0_scale = torch.sqrt(1.0 + self.sigmas[0] ** 2)
-        self.state = self.x_d * self.x0_scale
         self.h2d = sum(t.numel() * t.element_size() for t in [self.x_h, *self.c_h.values(), *self.uc_h.values()])
         self.d2h = self.out_h.numel() * self.out_h.element_size()
+        if fused:
+            self.plan = self.sampler.begin(self.denoiser, self.x_d.clone(), self.c_d, self.uc_d)
+            self.x_start = self.plan["x"].clone()
+            self.dedup = bool(self.plan["dedup"])
+        else:
+            self.state = self.x_d * self.x0_scale
+            self.dedup = False
 
     def _to_dev(self, d):
         return {k: v.to(self.dev, non_blocking=True) for k, v in d.items()}
@@ -156,15 +172,29 @@ class Workload:
         return self.sampler.sampler_step(self.s_in * self.sigmas[j], self.s_in * self.sigmas[j + 1], self.denoiser, x, c, uc)
 
     def resident_step(self, i):
+        if self.fused:
+            self.sampler.fused_step(self.plan, i % self.n_sched)
+            if (i + 1) % self.n_sched == 0:              # restart the schedule so values stay in range
+                self.plan["x"].copy_(self.x_start)
+            return
         self.state = self._step(i, self.state, self.c_d, self.uc_d)
-        if (i + 1) % self.n_sched == 0:                  # restart the schedule so values stay in range
+        if (i + 1) % self.n_sched == 0:
             self.state = self.x_d * self.x0_scale
 
     def e2e_step(self, i):
-        x = self.x_h.to(self.dev, non_blocking=True)
-        c, uc = self._to_dev(self.c_h), self._to_dev(self.uc_h)
-        y = self._step(i, x * self.x0_scale if i % self.n_sched == 0 else x, c, uc)
-        self.out_h.copy_(y, non_blocking=True)
+        """Host inputs in, host result out, every step: H2D of the latent and of both conditioning dicts from pinned
+        memory, one sampler step through the public API, D2H of the new latent, host synchronisation."""
+        if self.fused:
+            self.sampler.load_inputs(self.plan, x=self.x_h, cond=self.c_h, uc=self.uc_h)
+            if i % self.n_sched == 0:
+                self.plan["x"].mul_(self.x0_scale)
+            self.sampler.fused_step(self.plan, i % self.n_sched)
+            self.out_h.copy_(self.plan["x"], non_blocking=True)
+        else:
+            x = self.x_h.to(self.dev, non_blocking=True)
+            c, uc = self._to_dev(self.c_h), self._to_dev(self.uc_h)
+            y = self._step(i, x * self.x0_scale if i % self.n_sched == 0 else x, c, uc)
+            self.out_h.copy_(y, non_blocking=True)
         torch.cuda.current_stream().synchronize()        # the caller reads the result on the host every step
 
 
@@ -206,7 +236,9 @@ def run_ours(args):
         return parallel.max_over_ranks(e0.elapsed_time(e1), dev), ops.launch_count() - n0
 
     # `clips` clips per rank (clip-parallel, weak scaling): same shape, rank-specific seed
-    wl = Workload(wrap, dev, kind, clips, T, h, w, args.sampler_steps, args.cfg_scale, seed=100 + rank)
+    fused = args.sampler == "fused"
+    wl = Workload(wrap, dev, kind, clips, T, h, w, args.sampler_steps, args.cfg_scale, seed=100 + rank, fused=fused,
+                  graph=not args.no_graph, dedup=not args.no_dedup)
     warm = max(args.warmup, 3)
     for i in range(warm):                               # W >= 3 untimed warm-up steps (captures the CUDA graph)
         wl.resident_step(i)
@@ -232,6 +264,14 @@ def run_ours(args):
             "parallelism": f"clip-parallel x{world} (weights broadcast once, no step-loop collective)",
             "weights": f"random init, {n_params / 1e6:.1f} M params, fp16 kernel copies",
             "cuda_graph": not args.no_graph,
+            "sampler": ("FusedDPMPP2SAncestralSampler: 3 elementwise kernels + ONE CUDA graph per sampler step (both "
+                        "network calls inside)" if fused else "DPMPP2SAncestralSampler (PyTorch elementwise), one CUDA "
+                        "graph per network call"),
+            "cfg_dedup": wl.dedup,
+            "cfg_dedup_note": "the uncond and cond halves of the CFG batch share x, t and the hint: the layers ahead of "
+                              "the first text cross-attention (ControlNet hint stem + input blocks 0-1, UNet input blocks "
+                              "0-1 up to the self-attention) are computed once per call and fanned out; no result is "
+                              "cached across calls; network_call.executed_tflop counts what actually ran",
             "l2": "no explicit flush: every step streams 3.2 GB of weights and >100 MB activations per layer, "
                   "far beyond the 126 MB L2",
             "value_counts": "clip-steps per second: every rank advances `clips_per_gpu` clips by one sampler step per step",
@@ -249,12 +289,14 @@ def run_ours(args):
     # ---- per-kernel breakdown + roofline of the dominant kernel: one un-graphed network call, events per launch ----
     if rank == 0 and not args.no_breakdown:
         bd = kernel_breakdown(wrap, wl.x_d[:1], {k: v[:1] for k, v in wl.c_d.items()}, {k: v[:1] for k, v in wl.uc_d.items()},
-                              peaks, dev)
+                              peaks, dev, dedup=wl.dedup)
         result["network_call"].update(bd.pop("_flops"))
         result.update(bd)
     # ---- the other BASELINE.json configs, a few steps each (single GPU only: the scaling runs stay short) ----
     if rank == 0 and world == 1 and not args.no_configs and kind == "tv2v" and clips == 1:
         del wl
+        torch.cuda.empty_cache()
+        result["variants"] = variants(args, wrap, dev, timed, fused)
         result["configs"] = other_configs(args, wrap, dev, peaks, timed)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(kind, T, h, w, budget_s=args.cpu_budget, calls=1, warm=0)
@@ -263,6 +305,26 @@ def run_ours(args):
     parallel.barrier()
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def variants(args, wrap, dev, timed, fused):
+    """The headline workload with the optimisations of the sampler path switched off one at a time (a few steps each),
+    so that the headline can be read against the plain round-1 execution: PyTorch-elementwise sampler with one CUDA
+    graph per network call, and the fused step without CFG de-duplication."""
+    T, h, w = args.frames, args.height // 8, args.width // 8
+    out = {}
+    k = max(3, min(args.steps, 5))
+    for name, kw in (("plain_sampler_per_call_graph", dict(fused=False)), ("fused_step_no_cfg_dedup", dict(fused=True, dedup=False))):
+        if hasattr(wrap, "reset_graphs"):
+            wrap.reset_graphs()
+        torch.cuda.empty_cache()
+        wl = Workload(wrap, dev, args.kind, 1, T, h, w, args.sampler_steps, args.cfg_scale, seed=100, **kw)
+        for i in range(3):
+            wl.resident_step(i)
+        ms, _ = timed(wl.resident_step, k)
+        out[name] = {"steps": k, "ms_per_step": round(ms / k, 3), "value": round(k / (ms / 1e3), 4), "unit": UNIT}
+        del wl
+    return out
 
 
 def other_configs(args, wrap, dev, peaks, timed):
@@ -343,17 +405,18 @@ def ncu_traffic(kernel):
                                      "source": t.get("source")}
 
 
-def kernel_breakdown(wrap, x_d, c_d, uc_d, peaks, dev):
+def kernel_breakdown(wrap, x_d, c_d, uc_d, peaks, dev, dedup=False):
     from ccedit_b200 import ops
     cc = {k: torch.cat((uc_d[k], c_d[k]), 0) for k in c_d}
     x2 = torch.cat([x_d] * 2)
     t2 = torch.full((2,), 500, dtype=torch.long, device=dev)
+    call = (lambda: wrap.forward_cfg(x_d, t2[:1], cc)) if dedup else (lambda: wrap(x2, t2, cc))
     graph, wrap.use_cuda_graph = wrap.use_cuda_graph, False
     try:
-        wrap(x2, t2, cc)                                 # warm
+        call()                                           # warm
         torch.cuda.synchronize()
         ops.profile_start()
-        wrap(x2, t2, cc)
+        call()
         recs = ops.profile_stop(executed=True)
     finally:
         wrap.use_cuda_graph = graph
@@ -550,6 +613,9 @@ def main():
     ap.add_argument("--cfg-scale", type=float, default=7.5)
     ap.add_argument("--sampler-steps", type=int, default=30)
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of CUDA-graph replay")
+    ap.add_argument("--sampler", default="fused", choices=["fused", "plain"],
+                    help="fused: FusedDPMPP2SAncestralSampler (step graph); plain: PyTorch-elementwise sampler_step")
+    ap.add_argument("--no-dedup", action="store_true", help="fused sampler without CFG de-duplication")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2..4] section (tvi2v, 2 clips per GPU, sweep)")

@@ -94,6 +94,9 @@ SIGNATURES = {
     "ccedit_add_center_frame": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "ccedit_to_half": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ccedit_hint_stem01": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "ccedit_sampler_prepare": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "ccedit_sampler_mid": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp]),
+    "ccedit_sampler_final": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i64, _vp]),
 }
 
 _lib = None

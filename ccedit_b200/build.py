@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libccedit_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "norm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "hint_stem.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "norm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "hint_stem.cu",
+           "sampler.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "ccedit_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

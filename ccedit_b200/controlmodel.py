@@ -116,6 +116,7 @@ class UNetModel(nn.Module):
         self.num_classes = None
         self.num_heads, self.num_head_channels = num_heads, num_head_channels
         self.context_dim = context_dim
+        self.disable_text_ca = disable_text_ca
         self.pseudo3d = pseudo3d
         self.predict_codebook_ids = False
         self.dtype = torch.float16
@@ -308,12 +309,17 @@ class ControlNet2D(UNetModel):
             g = out
         return g
 
-    def forward_cl(self, x_cl: Optional[torch.Tensor], hint_cl: torch.Tensor, timesteps, context, B: int, T: int
-                   ) -> List[torch.Tensor]:
+    def forward_cl(self, x_cl: Optional[torch.Tensor], hint_cl: torch.Tensor, timesteps, context, B: int, T: int,
+                   cfg_dedup: bool = False) -> List[torch.Tensor]:
         """x_cl: [B*T, h, w, 8] (ignored if no_add_x); hint_cl: [B*T, 8h, 8w, 8] (or [B*T, h, w, 8] latent features when
-        the hint block is the identity).  Returns 13 channels-last tensors [B*T, h_l, w_l, C_l] (already * scale)."""
+        the hint block is the identity).  Returns 13 channels-last tensors [B*T, h_l, w_l, C_l] (already * scale).
+        cfg_dedup: B counts BOTH halves of a CFG batch (timesteps / context have B entries, uncond half first) but x_cl
+        and hint_cl hold only the B/2 * T frames the halves share; the layers ahead of the first text cross-attention
+        run once and fan out there (modules.SpatialTransformer.run_spatial)."""
         dev = hint_cl.device
         ctx = self._prepare_ctx(timesteps, context, B, T, dev)
+        if cfg_dedup and (self.disable_text_ca or len(self.input_blocks[1]) < 2):
+            raise RuntimeError("ccedit_b200: CFG de-duplication needs a text cross-attention in input block 1")
         conv_in = self.input_blocks[0][0].packed(dev)
         if self.set_input_hint_block_as_identity:
             F, H, W, _ = hint_cl.shape
@@ -329,9 +335,12 @@ class ControlNet2D(UNetModel):
                     h = guided
                 else:
                     h = ops.gemm(x_cl, conv_in, torch.empty_like(guided), ops.conv_taps(), res1=guided)
+            elif i == 1 and cfg_dedup:
+                h = module.run(h, ctx, dup=True)
             else:
                 h = module.run(h, ctx)
-            outs.append(self._zero_conv(zc[0], h))
+            o = self._zero_conv(zc[0], h)
+            outs.append(ops.dup_rows(o) if (i == 0 and cfg_dedup) else o)
         h = self.middle_block.run(h, ctx)
         outs.append(self._zero_conv(self.middle_block_out[0], h))
         return outs
@@ -392,11 +401,15 @@ class ControlledUNetModel3DTV2V(UNetModel):
         self._tail = None
 
     def forward_cl(self, x_cl: torch.Tensor, timesteps, context, control: Optional[List[torch.Tensor]],
-                   img_control: Optional[List[torch.Tensor]], only_mid_control: bool, out_dtype) -> torch.Tensor:
-        """x_cl: [B, T, h, w, 8]; control: 13 x [B*T, h_l, w_l, C_l] or None; img_control: 13 x [B, h_l, w_l, C_l]."""
+                   img_control: Optional[List[torch.Tensor]], only_mid_control: bool, out_dtype,
+                   cfg_dedup: bool = False) -> torch.Tensor:
+        """x_cl: [B, T, h, w, 8]; control: 13 x [B*T, h_l, w_l, C_l] or None; img_control: 13 x [B, h_l, w_l, C_l].
+        cfg_dedup: x_cl (and img_control) hold ONE copy of the B latents that the uncond and cond halves of a CFG batch
+        share, timesteps / context / control have 2 B entries (uncond first); input blocks 0 and 1 run once up to the
+        first text cross-attention and fan out there; the result has 2 B entries."""
         dev = x_cl.device
         B, T, H, W, _ = x_cl.shape
-        ctx = self._prepare_ctx(timesteps, context, B, T, dev)
+        ctx = self._prepare_ctx(timesteps, context, 2 * B if cfg_dedup else B, T, dev)
         control = None if control is None else list(control)
         img_control = None if img_control is None else list(img_control)
         mc = self.model_channels
@@ -410,11 +423,16 @@ class ControlledUNetModel3DTV2V(UNetModel):
                 y4 = y.view(B, T, H * W, mc)
                 h = ops.gemm(y4, self.input_blocks_temporal[0].packed(dev), torch.empty_like(y4), ops.temporal_taps(3),
                              res1=y4).view(B, T, H, W, mc)
+            elif i == 1 and cfg_dedup:
+                h = module.run(h, ctx, dup=True)                    # [2B, T, H, W, C] from here on
+                B = 2 * B
+                if img_control is not None:
+                    img_control = [ops.dup_rows(ic.contiguous()) for ic in img_control]
             else:
                 h = module.run(h, ctx)
             if img_control is not None and not only_mid_control:
                 ops.add_center_frame(h, img_control.pop(0))
-            hs.append(h)
+            hs.append(ops.dup_rows(h) if (i == 0 and cfg_dedup) else h)
         h = self.middle_block.run(h, ctx)
         if img_control is not None:
             ops.add_center_frame(h, img_control.pop(0))

@@ -197,8 +197,11 @@ class BasicTransformerBlock(nn.Module):
         self.attn2 = CrossAttention(dim, context_dim, n_heads, d_head)
         self.norm1, self.norm2, self.norm3 = norm(dim), norm(dim), norm(dim)
 
-    def run(self, x, F, L, ctx: Ctx, sp=None):
-        """sp: (sum, sum of squares) partials of x written by the GEMM that produced it (ops.gemm(stats_out=)), or None."""
+    def run(self, x, F, L, ctx: Ctx, sp=None, dup=False):
+        """sp: (sum, sum of squares) partials of x written by the GEMM that produced it (ops.gemm(stats_out=)), or None.
+        dup: x holds ONE copy of frames that the uncond and cond halves of a CFG batch share (see
+        SpatialTransformer.run_spatial); everything up to the text cross-attention runs once, then the rows fan out and
+        the result has 2 * F frames."""
         dev, C, M = x.device, x.shape[1], x.shape[0]
         heads = self.attn1.heads
         # The three LayerNorms are folded into the GEMMs they feed.  Their row statistics come from the epilogue of the
@@ -211,6 +214,10 @@ class BasicTransformerBlock(nn.Module):
         o1 = self.attn1.to_out["0"].packed(dev)
         sp = torch.empty(M, ops.stats_slots(o1), 2, dtype=torch.float32, device=dev)
         x = ops.gemm(att.view(M, C), o1, _new(x, M, C), res1=x, stats_out=sp)
+        if dup:                                                # attn2 reads the text: from here the halves differ
+            x, sp = ops.dup_rows(x), ops.dup_rows(sp)
+            F, M = 2 * F, 2 * M
+            att = _new(x, F, L, C)
         q = ops.gemm(x, self.attn2.to_q.packed_ln(dev, self.norm2), _new(x, M, C), rowstats=sp)
         k, v = ctx.text_kv[id(self.attn2)]
         att = ops.attention(q.view(F, L, C), [KVSegment(k, v, div=ctx.T)], heads, att)
@@ -262,8 +269,11 @@ class SpatialTransformer(nn.Module):
     def text_attns(self):
         return [] if self.disable_text_ca else [self.transformer_blocks[0].attn2]
 
-    def run_spatial(self, x4, ctx: Ctx, out=None):
-        """x4: [F, H, W, C] (contiguous). Returns x + proj_out(block(proj_in(GN(x)))) as [F, H, W, C]."""
+    def run_spatial(self, x4, ctx: Ctx, out=None, dup=False):
+        """x4: [F, H, W, C] (contiguous). Returns x + proj_out(block(proj_in(GN(x)))) as [F, H, W, C].
+        dup (CFG de-duplication): x4 holds the F frames that the uncond and the cond half of the batch have in common
+        (same latent, timestep and hint; only the text differs): GN, proj_in and the self-attention run once, the rows
+        fan out in front of the text cross-attention and the result has 2 * F frames (uncond half first)."""
         dev = x4.device
         F, H, W, C = x4.shape
         L, M = H * W, F * H * W
@@ -277,16 +287,24 @@ class SpatialTransformer(nn.Module):
                 kv3 = kv.view(F, L, 2 * C)
                 return ops.attention(q.view(F, L, C), [KVSegment(kv3[..., :C], kv3[..., C:])], self.heads,
                                      _new(q, F, L, C)).view(M, C)
+            if dup:
+                raise RuntimeError("ccedit_b200: CFG de-duplication needs a text cross-attention block to fan out at")
             h = blk.run(h, attend, sp=sp)
         else:
-            h = blk.run(h, F, L, ctx, sp=sp)
+            h = blk.run(h, F, L, ctx, sp=sp, dup=dup)
+        if dup:                                                # residual x_in for both halves, written in place
+            if out is not None:
+                raise RuntimeError("ccedit_b200: de-duplicated transformer cannot write into a caller buffer")
+            out = ops.dup_rows(x4)
+            ops.gemm(h, self.proj_out.packed(dev), out.view(2 * M, C), res1=out.view(2 * M, C))
+            return out
         out = _new(x4, F, H, W, C) if out is None else out
         ops.gemm(h, self.proj_out.packed(dev), out.view(M, C) if out.is_contiguous() else out.flatten(0, 2),
                  res1=x4.view(M, C))
         return out
 
-    def run(self, x4, ctx: Ctx, out=None):
-        return self.run_spatial(x4, ctx, out)
+    def run(self, x4, ctx: Ctx, out=None, dup=False):
+        return self.run_spatial(x4, ctx, out, dup)
 
 
 class SpatialTransformer3D(SpatialTransformer):
@@ -307,12 +325,14 @@ class SpatialTransformer3D(SpatialTransformer):
             self.transformer_blocks_temporal_ca = nn.ModuleList([BasicTransformerSingleLayerBlock(inner, n_heads, d_head)])
             self.proj_out_temporal_ca = conv2d(inner, in_channels, 1, zero=True)
 
-    def run(self, x5, ctx: Ctx, out=None):
+    def run(self, x5, ctx: Ctx, out=None, dup=False):
         dev = x5.device
         B, T, H, W, C = x5.shape
+        xs = self.run_spatial(x5.view(B * T, H, W, C), ctx, dup=dup)         # [F,H,W,C] (2 F frames after a fan-out)
+        if dup:
+            B *= 2
         F, L, M = B * T, H * W, B * T * H * W
         heads = self.heads
-        xs = self.run_spatial(x5.view(F, H, W, C), ctx)                     # [F,H,W,C]
         # ---- temporal attention over T per pixel (attention.py:1172-1207) ----
         xt = ops.groupnorm_temporal(xs.view(B, T, L, C), *self.norm_temporal.affine(dev), GN_EPS_ATTN, False)
         pin = self.proj_in_temporal.packed(dev)
@@ -504,8 +524,16 @@ class TimestepEmbedSequential(nn.ModuleList):
     def upsamples(self) -> bool:
         return any(isinstance(layer, Upsample3D) for layer in self)
 
-    def run(self, x, ctx: Ctx, out=None):
+    def run(self, x, ctx: Ctx, out=None, dup=False):
+        """dup: x is the de-duplicated half of a CFG batch; the block's transformer fans it out (see
+        SpatialTransformer.run_spatial), layers ahead of it run once."""
         n = len(self)
+        if dup and not any(isinstance(layer, SpatialTransformer) for layer in self):
+            raise RuntimeError("ccedit_b200: CFG de-duplication needs a transformer in the block")
         for i, layer in enumerate(self):
-            x = layer.run(x, ctx, out if i == n - 1 else None)
+            if dup and isinstance(layer, SpatialTransformer):
+                x = layer.run(x, ctx, out if i == n - 1 else None, dup=True)
+                dup = False
+            else:
+                x = layer.run(x, ctx, out if i == n - 1 else None)
         return x

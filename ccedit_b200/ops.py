@@ -557,6 +557,24 @@ def add_rows(a: torch.Tensor, b: Optional[torch.Tensor], dst: torch.Tensor) -> t
     return dst
 
 
+def dup_rows(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous tensor [d0, ...] -> [2 * d0, ...] holding t twice (raw 16-byte copies; any dtype).  Used by the CFG
+    de-duplication: layers whose inputs are identical in the uncond and cond halves run once and fan out here."""
+    if not t.is_cuda or not t.is_contiguous():
+        raise RuntimeError("ccedit_b200.dup_rows: t must be a contiguous CUDA tensor")
+    dst = torch.empty((2 * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    nbytes = t.numel() * t.element_size()
+    if nbytes % 16:
+        raise RuntimeError("ccedit_b200.dup_rows: size must be a multiple of 16 bytes")
+    n16 = nbytes // 2                                   # size in fp16 elements
+    C = next(c for c in (4096, 512, 64, 8) if n16 % c == 0)
+    M = n16 // C
+    for half in range(2):
+        _call("dup_rows", _lib.load().ccedit_add_rows,
+              (t.data_ptr(), C, None, 0, dst.data_ptr() + half * nbytes, C, M, C, _stream()), nbytes=2 * nbytes)
+    return dst
+
+
 def add_center_frame(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """x: [B, T, H, W, C] contiguous; y: [B, H, W, C]; x[:, T//2] += y in place."""
     _require(x, name="x")

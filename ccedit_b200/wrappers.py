@@ -58,6 +58,39 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
             img_control = net.controlnet_img.forward_cl(xc_cl, feat_cl.view(B, h, w, 8), t, crossattn, B, 1)
         return net.forward_cl(x_cl, t, crossattn, control, img_control, False, x.dtype)
 
+    def forward_cfg(self, x: torch.Tensor, t: torch.Tensor, c: dict) -> torch.Tensor:
+        """One network call for a classifier-free-guidance batch whose two halves share everything but the text:
+        x [B, 4, T, h, w] and t [B] are given ONCE, c["crossattn"] has 2 B entries (uncond first, guiders.py:56-67),
+        c["control_hint"] / c["cond_feat"] may have B or 2 B entries (the first B are used: the caller guarantees that
+        the halves are equal, as GeneralConditioner.get_unconditional_conditioning makes them).  Equivalent to
+        forward(cat([x] * 2), cat([t] * 2), c) -> eps [2 B, 4, T, h, w], but the layers ahead of the first text
+        cross-attention of the ControlNet and of the UNet (hint stem, input blocks 0 and 1 up to the self-attention:
+        ~7 % of a call's time at the headline shape) are computed once instead of twice.  Launches on the current
+        stream; capturable (the fused sampler step records it inside its step graph)."""
+        if not x.is_cuda:
+            raise RuntimeError("ccedit_b200: the network runs on CUDA (sm_100a) only; there is no CPU fallback")
+        net = self.diffusion_model
+        B, _, T, h, w = x.shape
+        crossattn, hint, feat = c["crossattn"], c["control_hint"][:B], c.get("cond_feat", None)
+        if crossattn.shape[0] != 2 * B:
+            raise RuntimeError(f"ccedit_b200.forward_cfg: crossattn must have 2 * {B} entries (uncond first)")
+        with torch.no_grad():
+            t2 = torch.cat([t] * 2)
+            x_cl = _to_cl(x, 8)
+            hint_cl = ops.ncthw_to_cl(hint, 8, pre=1.0, mul=-0.5, add=1.0)
+            control = net.controlnet.forward_cl(x_cl.view(B * T, h, w, 8),
+                                                hint_cl.view(B * T, hint_cl.shape[2], hint_cl.shape[3], 8), t2, crossattn,
+                                                2 * B, T, cfg_dedup=True)
+            img_control = None
+            if feat is not None:
+                if not net.controlnet_img.disable_text_ca:
+                    raise NotImplementedError("ccedit_b200.forward_cfg: controlnet_img with text cross-attention")
+                # controlnet_img has no text cross-attention (disable_text_ca): identical for both halves, computed once
+                feat_cl = _to_cl(feat[:B].unsqueeze(2), 8)
+                xc_cl = None if net.controlnet_img.no_add_x else x_cl[:, T // 2].contiguous()
+                img_control = net.controlnet_img.forward_cl(xc_cl, feat_cl.view(B, h, w, 8), t, None, B, 1)
+            return net.forward_cl(x_cl, t2, crossattn, control, img_control, False, x.dtype, cfg_dedup=True)
+
     def _graphed(self, x, t, crossattn, control_hint, cond_feat):
         ins = dict(x=x, t=t, crossattn=crossattn, control_hint=control_hint, cond_feat=cond_feat)
         ins = {k: v for k, v in ins.items() if v is not None}

@@ -195,6 +195,46 @@ int ccedit_to_half(const float* src, void* dst, int64_t n, void* stream);
 int ccedit_hint_stem01(const void* x, void* y, const void* w0, const float* b0, const void* w1, const float* b1,
                        int32_t F, int32_t H, int32_t W, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Sampler step, fused: the elementwise math of DPMPP2SAncestralSampler.sampler_step
+ * (sampling.py:385-407) + DiscreteDenoiser / EpsScaling (denoiser.py:22-40, denoiser_scaling.py:16-22) + VanillaCFG
+ * (guiders.py:25-29, 56-67) around the two network calls of a step.  x, x2, x_euler, noise, x_out: fp32 [n] latents
+ * (n = B*4*T*h*w); xin2 / eps2: fp32 [2n] network input / output at CFG batch 2B (uncond half first); t2: int64 [2B]
+ * timestep indices of the next network call.  sc: fp32 device table [steps][CCEDIT_SAMPLER_ROW] of per-step scalars
+ * (columns below), step: device int32 selecting the row - so a captured CUDA graph of a whole step replays for every step.
+ * Every operation is an individually rounded fp32 op in the reference's order: results are bit-identical to the unfused
+ * PyTorch formulas given the same scalars.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define CCEDIT_SAMPLER_ROW 16
+#define CCEDIT_SC_CIN1 0        /* 1 / sqrt(sigma_hat^2 + 1) of call 1 (sigma_hat = nearest entry of the 1000-sigma table) */
+#define CCEDIT_SC_COUT1 1       /* -sigma_hat of call 1 */
+#define CCEDIT_SC_IDX1 2        /* timestep index of call 1 */
+#define CCEDIT_SC_SIGMA 3       /* sigma of the step */
+#define CCEDIT_SC_DSIGMA 4      /* sigma_down - sigma */
+#define CCEDIT_SC_M1 5          /* get_mult: to_sigma(s) / to_sigma(t) */
+#define CCEDIT_SC_M2 6          /* expm1(-h / 2) */
+#define CCEDIT_SC_CIN2 7
+#define CCEDIT_SC_COUT2 8
+#define CCEDIT_SC_IDX2 9
+#define CCEDIT_SC_M3 10         /* to_sigma(t_next) / to_sigma(t) */
+#define CCEDIT_SC_M4 11         /* expm1(-h) */
+#define CCEDIT_SC_SIGMA_DOWN 12
+#define CCEDIT_SC_NEXT_SIGMA 13
+#define CCEDIT_SC_SIGMA_UP 14
+#define CCEDIT_SC_EULER_ONLY 15 /* 1 when sum(sigma_down) < 1e-14 (sampling.py:390): no second network call */
+/* xin2[0:n] = xin2[n:2n] = x * c_in1; t2 = idx1. */
+int ccedit_sampler_prepare(const float* x, float* xin2, int64_t* t2, const float* sc, const int32_t* step, int64_t n,
+                           int32_t B, void* stream);
+/* eps2 = network output of call 1: d = CFG(eps2 * c_out1 + x); x_euler = x + (x - d) / sigma * (sigma_down - sigma);
+ * x2 = m1 x - m2 d; xin2 = cat([x2 * c_in2] * 2); t2 = idx2. */
+int ccedit_sampler_mid(const float* x, const float* eps2, float* x_euler, float* x2, float* xin2, int64_t* t2,
+                       const float* sc, const int32_t* step, float cfg_scale, int64_t n, int32_t B, void* stream);
+/* eps2 = network output of call 2 (ignored when the row is Euler-only): d2 = CFG(eps2 * c_out2 + x2);
+ * x' = sigma_down > 0 ? m3 x - m4 d2 : x_euler; x_out = next_sigma > 0 ? x' + noise * s_noise * sigma_up : x'. */
+int ccedit_sampler_final(const float* x, const float* x2, const float* x_euler, const float* eps2, const float* noise,
+                         float* x_out, const float* sc, const int32_t* step, float cfg_scale, float s_noise, int64_t n,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif
