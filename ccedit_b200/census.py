@@ -142,3 +142,37 @@ def network_flops(kind: str, B: int, T: int, h: int, w: int, context_len: int = 
     f = dict(f)
     f["total"] = sum(f.values())
     return f
+
+
+def decoder_flops(F: int, h: int, w: int, ch: int = 128, ch_mult=(1, 2, 4, 4), num_res_blocks: int = 2, z_channels: int = 4,
+                  out_ch: int = 3) -> Dict[str, float]:
+    """Algorithmic FLOPs (2 x MACs of every conv / bmm, as FlopCounterMode counts the reference module) of
+    AutoencoderKL.decode on F frames of latent h x w: post_quant_conv + Decoder.forward (model.py:728-761)."""
+    f = defaultdict(float)
+    L = h * w
+    block_in = ch * ch_mult[-1]
+    f["conv1x1"] += 2.0 * F * L * z_channels * z_channels                                   # post_quant_conv
+    f["conv3x3"] += 2.0 * F * L * 9 * z_channels * block_in                                 # conv_in
+
+    def res(cin, cout, px):
+        f["conv3x3"] += 2.0 * F * px * 9 * (cin * cout + cout * cout)
+        if cin != cout:
+            f["conv1x1"] += 2.0 * F * px * cin * cout
+
+    res(block_in, block_in, L)
+    f["conv1x1"] += 4 * 2.0 * F * L * block_in * block_in                                   # q, k, v, proj_out
+    f["attention"] += 4.0 * F * L * L * block_in
+    res(block_in, block_in, L)
+    px = L
+    for i_level in reversed(range(len(ch_mult))):
+        block_out = ch * ch_mult[i_level]
+        for _ in range(num_res_blocks + 1):
+            res(block_in, block_out, px)
+            block_in = block_out
+        if i_level != 0:
+            px *= 4
+            f["conv3x3"] += 2.0 * F * px * 9 * block_in * block_in                          # Upsample.conv
+    f["conv3x3"] += 2.0 * F * px * 9 * block_in * out_ch                                    # conv_out
+    f = dict(f)
+    f["total"] = sum(f.values())
+    return f

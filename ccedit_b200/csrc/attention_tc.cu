@@ -50,6 +50,7 @@ struct FaTcParams {
   int lq, d;
   float scale_log2;
   int hpc;            // heads per CTA (> 1 for short key sequences: amortises the CTA set-up, overlaps the next Q load)
+  int dev;            // developer switches (CCEDIT_ATTN_DEV): 1 = folded kernel without the lo query block, 2 = without barrier probes
   long long* trace;   // diagnostics (ccedit_gemm_trace): per-tile phase clocks of CTA 0, or nullptr
 };
 
@@ -529,8 +530,8 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
   extern __shared__ uint8_t fa_smem_raw[];
   const uint32_t raw_addr = smem_u32(fa_smem_raw);
   uint8_t* smem = fa_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;                                    // [128][128 B]
-  uint8_t* sKV = smem + Cfg::QBytes;                     // stages x (K [KT][128 B], V [KT][128 B])
+  uint8_t* sQ = smem;                                    // [2][128][128 B]: hi and lo halves of scale*log2e*q (see q load)
+  uint8_t* sKV = smem + 2 * Cfg::QBytes;                 // stages x (K [KT][128 B], V [KT][128 B])
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kT2Stages * 2 * Cfg::KBytes);
   uint64_t* kv_full = bars;
   uint64_t* kv_empty = bars + kT2Stages;
@@ -617,8 +618,9 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
     {
       const uint32_t sKa = smem_u32(sKV);
 #pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks)
-        umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa) + 2u * ks, umma_desc_k_sw128(sKa) + 2u * ks, idesc_s, ks ? 1u : 0u);
+      for (int ks = 0; ks < 2 * KSTEPS; ++ks)            // S = Qhi K^T + Qlo K^T: both Q blocks against the same K tile
+        if (ks < KSTEPS || !(p.dev & 1)) umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa + (ks >= KSTEPS ? Cfg::QBytes : 0)) + 2u * (ks % KSTEPS),
+                         umma_desc_k_sw128(sKa) + 2u * (ks % KSTEPS), idesc_s, ks ? 1u : 0u);
       umma_commit_warp(s_full);
     }
     int stage = 0;
@@ -638,8 +640,9 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
         tcgen05_fence_after();
         const uint32_t sKa = smem_u32(sKV + nstage * 2 * Cfg::KBytes);
 #pragma unroll
-        for (int ks = 0; ks < KSTEPS; ++ks)
-          umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa) + 2u * ks, umma_desc_k_sw128(sKa) + 2u * ks, idesc_s, ks ? 1u : 0u);
+        for (int ks = 0; ks < 2 * KSTEPS; ++ks)
+          if (ks < KSTEPS || !(p.dev & 1)) umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa + (ks >= KSTEPS ? Cfg::QBytes : 0)) + 2u * (ks % KSTEPS),
+                           umma_desc_k_sw128(sKa) + 2u * (ks % KSTEPS), idesc_s, ks ? 1u : 0u);
         umma_commit_warp(s_full);
       }
       const uint64_t dV = umma_desc_mn_sw128(smem_u32(sKV + stage * 2 * Cfg::KBytes + Cfg::KBytes), KT * 128);
@@ -664,7 +667,9 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
     // the -mref slot of this thread's query row (channel d)
     uint16_t* qm = reinterpret_cast<uint16_t*>(qrow_smem + ((((d >> 3) ^ sw)) << 4) + (d & 7) * 2);
     if (half == 0) {
-      // Q row -> registers -> * scale*log2(e) -> fp16 -> swizzled shared memory; channels >= d zero (-mref = 0 to begin with)
+      // Q row -> registers -> * scale*log2(e) -> fp16 hi + fp16 lo (the rounding residual of hi: the scaled query keeps
+      // ~22 significant bits, as accurate as scaling the fp32 scores) -> two swizzled operand blocks in shared memory;
+      // channels >= d zero (-mref = 0 to begin with)
       const int chunks = d >> 3;
       const int qrow = q0 + row;
       const bool ok = qrow < p.lq;
@@ -672,18 +677,24 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
                           static_cast<long long>(head) * d;
 #pragma unroll 1
       for (int ch = 0; ch < 2 * KSTEPS; ++ch) {
-        uint4 u = make_uint4(0, 0, 0, 0);
+        uint4 u = make_uint4(0, 0, 0, 0), ul = make_uint4(0, 0, 0, 0);
         if (ch < chunks && ok) {
           u = __ldg(reinterpret_cast<const uint4*>(src) + ch);
-          uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          uint32_t w[4] = {u.x, u.y, u.z, u.w}, wl[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-            w[j] = pack_h2(v.x * c, v.y * c);
+            const float px = v.x * c, py = v.y * c;
+            const __half2 hi = __floats2half2_rn(px, py);
+            const float2 hf = __half22float2(hi);
+            w[j] = *reinterpret_cast<const uint32_t*>(&hi);
+            wl[j] = pack_h2(px - hf.x, py - hf.y);
           }
           u = make_uint4(w[0], w[1], w[2], w[3]);
+          ul = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
         *reinterpret_cast<uint4*>(qrow_smem + (((ch & 7) ^ sw) << 4)) = u;
+        *reinterpret_cast<uint4*>(qrow_smem + Cfg::QBytes + (((ch & 7) ^ sw) << 4)) = ul;
       }
       fence_proxy_async_smem();
       mbar_arrive(q_full);
@@ -697,11 +708,14 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
     float mref = -INFINITY;            // row reference (fp16-representable once set); identical in both halves
     float mq = 0.f;                    // value the -mref channel of Q currently encodes (as +mref)
     float mb_next = 0.f;               // reference baked into S(it + 1)
+    bool s_ready = false;              // S(it) was already seen complete by the probe at the end of the previous tile
     for (int it = 0; it < total; ++it) {
       const int par = it & 1;
       const int seg = it < p.ntile[0] ? 0 : 1;
       const int valid = p.lkv[seg] - (seg == 0 ? it : it - p.ntile[0]) * KT - HK * half;
-      mbar_wait(s_full, static_cast<uint32_t>(par));
+      // an mbarrier wait costs ~100-200 clocks even when its phase completed long ago (TRYWAIT latency): S(it) is probed
+      // with a non-blocking test issued under the previous tile's last stores, the blocking wait is the fallback
+      if (!s_ready) mbar_wait(s_full, static_cast<uint32_t>(par));
       tcgen05_fence_after();
       const float mb = mb_next;                          // reference baked into this tile's scores
       if (mref != mq && mref != -INFINITY) {             // S(it) has been computed: Q may change for S(it + 1)
@@ -736,6 +750,8 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
       sm[half * 128] = mloc;
       named_bar_arrive(1 + 2 * half + par, 256);          // published; nobody waits here
       bool owait = it > 0;                               // P / O still belong to P.V of the previous tile
+      // same trick for P.V(it - 1): probe now, consume the answer at the first P store that needs it
+      const bool o_ready = it > 0 && !(p.dev & 2) && mbar_test_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
       // ---- P from the scores: x = r + delta, delta = 0 when the baked reference is current ----
       auto emit_p = [&](float delta, bool shifted) {
 #pragma unroll
@@ -760,7 +776,7 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
           }
           const bool alt = kPx && half == 0 && cc == 0;   // the first 32 keys of P have a second buffer (odd tiles)
           if (owait && !alt) {
-            mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
+            if (!o_ready) mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
             tcgen05_fence_after();
             owait = false;
           }
@@ -782,7 +798,7 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
         }
         if (it > 0 && __any_sync(0xffffffffu, need)) {    // O (and the row sum in its column d) move to the new reference
           if (owait) {
-            mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
+            if (!o_ready) mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
             tcgen05_fence_after();
             owait = false;
           }
@@ -798,6 +814,7 @@ flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_co
         }
         emit_p(mb - mref, true);
       }
+      s_ready = it + 1 < total && !(p.dev & 2) && mbar_test_wait(s_full, static_cast<uint32_t>(par ^ 1));   // S(it + 1), see the loop head
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(p_full);
@@ -901,7 +918,7 @@ static int launch_tc2_t(const CUtensorMap* maps, const FaTcParams& p, int frames
 
 template <int KSTEPS, int EMU>
 static int launch_fold(const CUtensorMap* maps, const FaTcParams& p, int frames, int heads, cudaStream_t st) {
-  const int smem = T2Cfg<KSTEPS>::Smem;
+  const int smem = T2Cfg<KSTEPS>::Smem + T2Cfg<KSTEPS>::QBytes;      // second (lo) block of the scaled query
   static std::atomic<bool> attr_set[kMaxDevices];
   const int dev = current_device();
   CCEDIT_CHECK_ARG(dev >= 0, "ccedit_attention(fold): no current CUDA device");
@@ -969,6 +986,8 @@ int attention_tc(const ccedit_attn_desc* a, cudaStream_t st) {
   p.d = a->d;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.trace = g_trace_buf;
+  static const int attn_dev = [] { const char* e = getenv("CCEDIT_ATTN_DEV"); return e ? atoi(e) : 0; }();
+  p.dev = attn_dev;
   // Heads per CTA: with one or two key tiles per head (text cross-attention: 77 keys) a CTA's life is all set-up
   // (TMEM allocation, barrier init, descriptor fetch, Q / K / V latency: ~6 us for ~1.5 us of work), so it takes several
   // heads in a row as long as enough CTAs remain to fill the 2 x 148 slots a few times over.

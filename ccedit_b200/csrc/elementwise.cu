@@ -336,3 +336,136 @@ extern "C" int ccedit_to_half(const float* src, void* dst, int64_t n, void* stre
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_to_half");
   return CCEDIT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// First-stage (VAE) helpers
+// ---------------------------------------------------------------------------------------------------------------
+namespace ccedit {
+
+// In-place softmax over the N columns of every row of a row-major fp16 matrix (fp32 arithmetic): the middle step of the
+// first-stage decoder's single-head d = 512 attention (model.py:161-201), which runs as GEMM -> softmax -> GEMM because
+// one head of width 512 does not fit the flash kernel's TMEM budget.  One CTA per row, the row lives in registers.
+template <int VPT>      // 16-byte vectors per thread
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long long ld, int N) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  __half* row = x + static_cast<long long>(blockIdx.x) * ld;
+  const int nvec = N >> 3;
+  float v[VPT][8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int iv = threadIdx.x + 256 * i;
+    if (iv < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + iv * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        v[i][2 * j] = f.x;
+        v[i][2 * j + 1] = f.y;
+        m = fmaxf(m, fmaxf(f.x, f.y));
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int k = 1; k < 8; ++k) t = fmaxf(t, red[k]);
+    bcast = t;
+  }
+  __syncthreads();
+  m = bcast;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    if (threadIdx.x + 256 * i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] = __expf(v[i][j] - m);
+        s += v[i][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];             // fixed order: deterministic
+    bcast = 1.f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int iv = threadIdx.x + 256 * i;
+    if (iv < nvec) {
+      uint4 u;
+      __half2 h0 = __floats2half2_rn(v[i][0] * inv, v[i][1] * inv), h1 = __floats2half2_rn(v[i][2] * inv, v[i][3] * inv);
+      __half2 h2 = __floats2half2_rn(v[i][4] * inv, v[i][5] * inv), h3 = __floats2half2_rn(v[i][6] * inv, v[i][7] * inv);
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2);
+      u.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(row + iv * 8) = u;
+    }
+  }
+}
+
+// channels-last fp16 [B][T][HW][ld] (first C channels) -> [B][C][T][HW] fp32 / fp16: the decoder's image output
+template <typename DstT>
+__global__ void cl_to_ncthw_kernel(const __half* __restrict__ src, int ld, DstT* __restrict__ dst, int C, int T, long long HW,
+                                   long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over B*T*HW
+  if (i >= total) return;
+  const long long hw = i % HW, bt = i / HW;
+  const int t = static_cast<int>(bt % T);
+  const long long b = bt / T;
+  const __half* s = src + i * ld;
+  for (int c = 0; c < C; ++c) dst[((b * C + c) * T + t) * HW + hw] = static_cast<DstT>(__half2float(s[c]));
+}
+
+}  // namespace ccedit
+
+extern "C" int ccedit_softmax_rows(void* x, int64_t ld, int64_t M, int32_t N, void* stream) {
+  CCEDIT_CHECK_ARG(x && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0 && ld >= N && N <= 8 * 256 * 8,
+                   "ccedit_softmax_rows: bad shape M=%lld N=%d ld=%lld (N %% 8 == 0, N <= 16384)", (long long)M, N, (long long)ld);
+  CCEDIT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "ccedit_softmax_rows: x must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __half* xp = static_cast<__half*>(x);
+  const unsigned grid = static_cast<unsigned>(M);
+  const int vpt = (N / 8 + 255) / 256;
+  switch (vpt) {
+    case 1: softmax_rows_kernel<1><<<grid, 256, 0, st>>>(xp, ld, N); break;
+    case 2: softmax_rows_kernel<2><<<grid, 256, 0, st>>>(xp, ld, N); break;
+    case 3: softmax_rows_kernel<3><<<grid, 256, 0, st>>>(xp, ld, N); break;
+    case 4: softmax_rows_kernel<4><<<grid, 256, 0, st>>>(xp, ld, N); break;
+    default: softmax_rows_kernel<8><<<grid, 256, 0, st>>>(xp, ld, N); break;
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_softmax_rows");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_cl_to_ncthw(const void* src, int32_t ld, void* dst, int32_t dst_f32, int32_t B, int32_t C, int32_t T,
+                                  int64_t HW, void* stream) {
+  CCEDIT_CHECK_ARG(src && dst && B > 0 && C > 0 && T > 0 && HW > 0 && ld >= C, "ccedit_cl_to_ncthw: bad arguments");
+  const long long total = static_cast<long long>(B) * T * HW;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dst_f32)
+    cl_to_ncthw_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(src), ld, static_cast<float*>(dst),
+                                                                      C, T, HW, total);
+  else
+    cl_to_ncthw_kernel<__half><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(src), ld,
+                                                                       static_cast<__half*>(dst), C, T, HW, total);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_cl_to_ncthw");
+  return CCEDIT_OK;
+}

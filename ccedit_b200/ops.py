@@ -641,3 +641,52 @@ def note_graph_replay(n: int) -> None:
 def launch_count() -> int:
     """Kernels of this library executed so far in this process (direct launches + graph-replayed launches)."""
     return _lib.launch_count() + _GRAPH_LAUNCHES
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# first-stage (VAE) helpers
+# ---------------------------------------------------------------------------------------------------------------------
+def softmax_rows(x: torch.Tensor) -> torch.Tensor:
+    """x: fp16 [M, N] (row stride free, N contiguous): row softmax in place, fp32 arithmetic."""
+    _require(x, name="x")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise RuntimeError("ccedit_b200.softmax_rows: x must be [M, N] with contiguous columns")
+    M, N = x.shape
+    _call("softmax_rows", _lib.load().ccedit_softmax_rows, (x.data_ptr(), x.stride(0), M, N, _stream()), nbytes=2 * _nb(x))
+    return x
+
+
+def cl_to_ncthw(y: torch.Tensor, cout: int, out_dtype=torch.float32) -> torch.Tensor:
+    """y: channels-last fp16 [B, T, H, W, ld] -> [B, cout, T, H, W] (first cout channels)."""
+    _require(y, name="y")
+    if not y.is_contiguous():
+        raise RuntimeError("ccedit_b200.cl_to_ncthw: y must be contiguous")
+    B, T, H, W, ld = y.shape
+    dst = torch.empty(B, cout, T, H, W, dtype=out_dtype, device=y.device)
+    _call("cl_to_ncthw", _lib.load().ccedit_cl_to_ncthw,
+          (y.data_ptr(), ld, dst.data_ptr(), int(out_dtype == torch.float32), B, cout, T, H * W, _stream()), nbytes=_nb(y, dst))
+    return dst
+
+
+def activation_as_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedWeight:
+    """A contiguous fp16 activation matrix [N, K] (K % 64 == 0) used as the weight operand of ``gemm`` - the K / V^T
+    operands of a GEMM-formulated attention."""
+    _require(w, name="w")
+    if w.dim() != 2 or not w.is_contiguous() or w.shape[1] % BLOCK_K:
+        raise RuntimeError("ccedit_b200.activation_as_weight: w must be contiguous [N, K] with K a multiple of 64")
+    n, k = w.shape
+    return PackedWeight(w, bias, n, k, k, 1, pick_bn(n))
+
+
+def conv_s2_taps_asym():
+    """3x3, stride 2, NO padding on the top/left and one zero row/column on the bottom/right (the first stage's
+    Downsample, model.py:83-91: F.pad(x, (0, 1, 0, 1)) + conv stride 2 padding 0) over the 4 parity planes of
+    ``parity_split``: input index 2*o + k -> (parity, offset) = (0, 0), (1, 0), (0, +1)."""
+    split = lambda k: (0, 0) if k == 0 else ((1, 0) if k == 1 else (0, 1))
+    taps = []
+    for kh in range(3):
+        ph, oh = split(kh)
+        for kw in range(3):
+            pw, ow = split(kw)
+            taps.append((ow, oh, ph * 2 + pw, 0))
+    return taps

@@ -196,6 +196,17 @@ int ccedit_hint_stem01(const void* x, void* y, const void* w0, const float* b0, 
                        int32_t F, int32_t H, int32_t W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * First stage (VAE): helpers next to ccedit_gemm / ccedit_groupnorm_spatial / ccedit_upsample_nearest2x.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* In-place softmax over the N columns of each of the M rows of a row-major fp16 matrix (row stride ld elements), fp32
+ * arithmetic: the middle of AttnBlock's single-head d = 512 attention (model.py:161-201), run as GEMM -> softmax -> GEMM. */
+int ccedit_softmax_rows(void* x, int64_t ld, int64_t M, int32_t N, void* stream);
+/* channels-last fp16 [B][T][HW][ld] (first C channels valid) -> [B][C][T][HW], fp32 if dst_f32 else fp16: the decoded
+ * image in the reference's "b c t h w" layout (autoencoder.py:341-342). */
+int ccedit_cl_to_ncthw(const void* src, int32_t ld, void* dst, int32_t dst_f32, int32_t B, int32_t C, int32_t T, int64_t HW,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Sampler step, fused: the elementwise math of DPMPP2SAncestralSampler.sampler_step
  * (sampling.py:385-407) + DiscreteDenoiser / EpsScaling (denoiser.py:22-40, denoiser_scaling.py:16-22) + VanillaCFG
  * (guiders.py:25-29, 56-67) around the two network calls of a step.  x, x2, x_euler, noise, x_out: fp32 [n] latents

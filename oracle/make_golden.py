@@ -206,10 +206,67 @@ def run_full(kind, names):
         torch.save(store, path)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# first stage: the reference's Decoder / Encoder classes (sgm/modules/diffusionmodules/model.py) with
+# the ddconfig of the inference YAML, wrapped the way AutoencoderKL does (post_quant_conv / quant_conv, autoencoder.py
+# :296-319; the class itself cannot be imported: it derives from pytorch_lightning.LightningModule).
+#   python -m oracle.make_golden vae
+# ---------------------------------------------------------------------------------------------------------------------
+def run_vae():
+    import torch.nn as nn
+    ref_import.install_shim()
+    from sgm.modules.diffusionmodules.model import Decoder, Encoder
+    from oracle.vae_oracle import DDCONFIG, SCALE_FACTOR
+    t0 = time.time()
+
+    class FirstStage(nn.Module):                        # AutoencoderKL.__init__, autoencoder.py:283-303
+        def __init__(self):
+            super().__init__()
+            with contextlib.redirect_stdout(io.StringIO()):
+                self.encoder = Encoder(**DDCONFIG)
+                self.decoder = Decoder(**DDCONFIG)
+            self.quant_conv = nn.Conv2d(2 * DDCONFIG["z_channels"], 2 * 4, 1)
+            self.post_quant_conv = nn.Conv2d(4, DDCONFIG["z_channels"], 1)
+
+    fs = FirstStage().eval()
+    man = manifest_of(fs)
+    with open(os.path.join(GOLDEN_DIR, "manifest_vae.json"), "w") as f:
+        json.dump(man, f)
+    fs.load_state_dict(seeded_state_dict(man, seed=0), strict=True)
+    dec, enc = fs.decoder, fs.encoder
+    out = {}
+    with torch.no_grad():
+        def rec(name, mod, x, prefix, *extra):
+            out[name] = dict(prefix=prefix, inputs=[x.clone()], output=mod(x, *extra).clone())
+
+        rec("res_512", dec.mid.block_1, rnd(2, 512, 8, 12, seed=61), "decoder.mid.block_1", None)
+        rec("res_256_128", dec.up[0].block[0], rnd(1, 256, 16, 24, seed=62), "decoder.up.0.block.0", None)
+        rec("attn_512", dec.mid.attn_1, rnd(2, 512, 16, 12, seed=63), "decoder.mid.attn_1")
+        rec("attn_512_big", dec.mid.attn_1, rnd(1, 512, 32, 40, seed=64) * 2.0, "decoder.mid.attn_1")
+        rec("up_512", dec.up[3].upsample, rnd(1, 512, 6, 8, seed=65), "decoder.up.3.upsample")
+        rec("down_128", enc.down[0].downsample, rnd(2, 128, 16, 24, seed=66), "encoder.down.0.downsample")
+        # decode_first_stage (diffusion.py:152-156) on a video latent: 2 frames of 8x12 -> 64x96 pixels
+        z = rnd(1, 4, 2, 8, 12, seed=67)
+        zz = (1.0 / SCALE_FACTOR * z).permute(0, 2, 1, 3, 4).reshape(2, 4, 8, 12)
+        d = dec(fs.post_quant_conv(zz))
+        out["decode_video"] = dict(inputs=[z], output=d.reshape(1, 2, 3, 64, 96).permute(0, 2, 1, 3, 4).clone())
+        # one frame at a latent whose token count is not a multiple of 128 (mid attention tails)
+        z1 = rnd(1, 4, 1, 16, 24, seed=68)
+        d1 = dec(fs.post_quant_conv((1.0 / SCALE_FACTOR * z1)[:, :, 0]))
+        out["decode_frame"] = dict(inputs=[z1], output=d1[:, :, None].clone())
+        # encoder moments (quant_conv(encoder(x))) on 2 frames of 64x96 pixels
+        x = torch.rand(2, 3, 64, 96, generator=torch.Generator().manual_seed(69)) * 2 - 1
+        out["encode_moments"] = dict(inputs=[x], output=fs.quant_conv(enc(x)).clone())
+    torch.save(out, os.path.join(GOLDEN_DIR, "vae.pt"))
+    print("vae fixtures done", round(time.time() - t0, 1), "s", {k: tuple(v["output"].shape) for k, v in out.items()}, flush=True)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
-    if len(sys.argv) > 1 and sys.argv[1] == "full":
+    if len(sys.argv) > 1 and sys.argv[1] == "vae":
+        run_vae()
+    elif len(sys.argv) > 1 and sys.argv[1] == "full":
         run_full(sys.argv[2], sys.argv[3:] or list(FULL_CASES))
     else:
         for kind in (sys.argv[1:] or ["tv2v", "tvi2v"]):

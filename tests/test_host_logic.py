@@ -36,6 +36,21 @@ def test_state_dict_layout_matches_reference(kind, manifests):
         assert hasattr(net, "controlnet_img") and net.ca_type == "center_self"
 
 
+def test_first_stage_state_dict_layout_matches_reference():
+    """ccedit_b200.autoencoder keeps the reference's first-stage keys and shapes (tests/golden/manifest_vae.json was
+    written from the reference's Encoder / Decoder / quant convs by oracle/make_golden.py vae)."""
+    from oracle.vae_oracle import DDCONFIG
+    from oracle.weights import load_manifest
+    from ccedit_b200.autoencoder import AutoencoderKLInferenceWrapper
+    sd = AutoencoderKLInferenceWrapper(ddconfig=dict(DDCONFIG), embed_dim=4).state_dict()
+    man = load_manifest("vae")
+    assert set(sd) == set(man)
+    for k, (shape, _) in man.items():
+        assert list(sd[k].shape) == shape, k
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        AutoencoderKLInferenceWrapper(ddconfig=dict(DDCONFIG), embed_dim=4).decode(torch.zeros(1, 4, 8, 8))
+
+
 def test_unsupported_configs_fail_loudly():
     from oracle.ref_import import yaml_params
     from ccedit_b200.controlmodel import ControlledUNetModel3DTV2V

@@ -8,6 +8,7 @@ import torch
 from conftest import load_golden, rel_err
 from oracle import inputs as oin
 from oracle import sgm_oracle as so
+from oracle import vae_oracle as vo
 
 TOL = 2e-5
 
@@ -136,3 +137,36 @@ def test_sampler_matches_reference(state_dicts):
     assert len(sigmas_seen) == g["n_calls"] == 2 * g["steps"] - 1
     assert torch.allclose(torch.stack(sigmas_seen), g["call_sigmas"], rtol=1e-6, atol=0)
     assert rel_err(out, g["output"]) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# first stage (oracle/vae_oracle.py) against the reference's Decoder / Encoder fixtures (tests/golden/vae.pt)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def vae_sd():
+    from oracle.weights import load_manifest, seeded_state_dict
+    return seeded_state_dict(load_manifest("vae"), seed=0)
+
+
+VAE_BLOCK_FN = {
+    "res_512": lambda sd, p, x: vo.resnet_block(sd, p, x), "res_256_128": lambda sd, p, x: vo.resnet_block(sd, p, x),
+    "attn_512": lambda sd, p, x: vo.attn_block(sd, p, x), "attn_512_big": lambda sd, p, x: vo.attn_block(sd, p, x),
+    "up_512": lambda sd, p, x: vo.upsample(sd, p, x), "down_128": lambda sd, p, x: vo.downsample(sd, p, x),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VAE_BLOCK_FN))
+def test_vae_block_matches_reference(name, vae_sd):
+    g = load_golden("vae.pt")[name]
+    with torch.no_grad():
+        out = VAE_BLOCK_FN[name](vae_sd, g["prefix"], g["inputs"][0])
+    assert rel_err(out, g["output"]) < TOL
+
+
+def test_vae_decode_and_encode_match_reference(vae_sd):
+    gold = load_golden("vae.pt")
+    with torch.no_grad():
+        for name in ("decode_video", "decode_frame"):
+            assert rel_err(vo.decode_first_stage(vae_sd, gold[name]["inputs"][0]), gold[name]["output"]) < TOL
+        g = gold["encode_moments"]
+        assert rel_err(vo.encode_first_stage_moments(vae_sd, g["inputs"][0]), g["output"]) < TOL
