@@ -387,6 +387,25 @@ def other_configs(args, wrap, dev, peaks, timed):
     wl = Workload(wrap3, dev, "tvi2v", 1, T, h, w, 50, 7.0, seed=400)
     out["config3_tvi2v"] = steps_entry(wl, "tvi2v", 1, T, h, w,
                                        "tvi2v ref-branch (cfca center_self) depthzoe, 17x512x768, 50-step schedule, cfg 7")
+    del wl, wrap3
+    torch.cuda.empty_cache()
+    # SURVEY 8 row f1 (next after the UNet): first-stage decode of the clip, once per clip after the last sampler step
+    from ccedit_b200.autoencoder import AutoencoderKLInferenceWrapper
+    from ccedit_b200.census import decoder_flops
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    with torch.device(dev):
+        vae = AutoencoderKLInferenceWrapper(ddconfig=dd, embed_dim=4).eval()
+    z = torch.randn(1, 4, T, h, w, generator=torch.Generator().manual_seed(9)).to(dev)
+    for _ in range(2):
+        vae.decode(z, scale=1.0 / 0.18215)
+    ms, _ = timed(lambda i: vae.decode(z, scale=1.0 / 0.18215), 3)
+    fl = decoder_flops(T, h, w)["total"]
+    tf = fl / (ms / 3 / 1e3) / 1e12
+    out["first_stage_decode"] = {"workload": f"AutoencoderKL.decode of {T} frames {args.height}x{args.width} (latent {h}x{w}), "
+                                             "fp16 storage / fp32 accumulation, eager launches",
+                                 "ms_per_clip": round(ms / 3, 3), "algorithmic_tflop": round(fl / 1e12, 2),
+                                 "achieved_tflops": round(tf, 1), "frac_of_measured_sustained_bf16": round(tf / peaks["sustained"], 4)}
     return out
 
 

@@ -310,12 +310,15 @@ class ControlNet2D(UNetModel):
         return g
 
     def forward_cl(self, x_cl: Optional[torch.Tensor], hint_cl: torch.Tensor, timesteps, context, B: int, T: int,
-                   cfg_dedup: bool = False) -> List[torch.Tensor]:
+                   cfg_dedup: bool = False, sinks=None) -> Optional[List[torch.Tensor]]:
         """x_cl: [B*T, h, w, 8] (ignored if no_add_x); hint_cl: [B*T, 8h, 8w, 8] (or [B*T, h, w, 8] latent features when
         the hint block is the identity).  Returns 13 channels-last tensors [B*T, h_l, w_l, C_l] (already * scale).
         cfg_dedup: B counts BOTH halves of a CFG batch (timesteps / context have B entries, uncond half first) but x_cl
         and hint_cl hold only the B/2 * T frames the halves share; the layers ahead of the first text cross-attention
-        run once and fan out there (modules.SpatialTransformer.run_spatial)."""
+        run once and fan out there (modules.SpatialTransformer.run_spatial).
+        sinks (ControlledUNetModel3DTV2V.control_sinks): the ControlNet residual add fused into the skip write
+        (controlmodel.py:536-543): zero conv j does not materialise control[j] but writes  zero_conv(h) * scale + skip
+        straight into the UNet decoder's concat buffer (epilogue residual); nothing is returned."""
         dev = hint_cl.device
         ctx = self._prepare_ctx(timesteps, context, B, T, dev)
         if cfg_dedup and (self.disable_text_ca or len(self.input_blocks[1]) < 2):
@@ -339,11 +342,29 @@ class ControlNet2D(UNetModel):
                 h = module.run(h, ctx, dup=True)
             else:
                 h = module.run(h, ctx)
+            if sinks is not None:
+                self._zero_conv_into(zc[0], h, sinks[i])
+                continue
             o = self._zero_conv(zc[0], h)
             outs.append(ops.dup_rows(o) if (i == 0 and cfg_dedup) else o)
         h = self.middle_block.run(h, ctx)
+        if sinks is not None:
+            self._zero_conv_into(self.middle_block_out[0], h, sinks[-1])
+            return None
         outs.append(self._zero_conv(self.middle_block_out[0], h))
         return outs
+
+    def _zero_conv_into(self, holder: ParamHolder, h: torch.Tensor, sink) -> None:
+        """sink: [(dst, res)] - dst a channel slice of a concat buffer, res the UNet skip (same rows as h)."""
+        from .modules import _as2d
+        pw = holder.packed(h.device, scale=float(self.control_scales))
+        F, H, W, C = h.shape
+        M = F * H * W
+        for dst, res in sink:
+            if dst.numel() != M * pw.n or res.numel() != M * pw.n:
+                raise RuntimeError("ccedit_b200: control sink does not match the ControlNet output "
+                                   f"({tuple(dst.shape)} / {tuple(res.shape)} vs {(F, H, W, pw.n)})")
+            ops.gemm(h.view(M, C), pw, _as2d(dst, M, pw.n), res1=res.reshape(M, pw.n))
 
     def _zero_conv(self, holder: ParamHolder, h: torch.Tensor) -> torch.Tensor:
         pw = holder.packed(h.device, scale=float(self.control_scales))
@@ -407,10 +428,25 @@ class ControlledUNetModel3DTV2V(UNetModel):
         cfg_dedup: x_cl (and img_control) hold ONE copy of the B latents that the uncond and cond halves of a CFG batch
         share, timesteps / context / control have 2 B entries (uncond first); input blocks 0 and 1 run once up to the
         first text cross-attention and fan out there; the result has 2 B entries."""
+        hs, h, ctx = self.encode_cl(x_cl, timesteps, context, img_control, only_mid_control, cfg_dedup)
+        if cfg_dedup:
+            hs[0] = ops.dup_rows(hs[0])
+        cats = self.decoder_buffers(hs, h)
+        # decoder input: h = cat([h, hs.pop() + control.pop()], 1) (controlmodel.py:536-544); control = None: plain copies
+        control = None if control is None else list(control)
+        ops.add_rows(h, control.pop() if control is not None else None, cats[0][..., :h.shape[-1]])
+        for i in range(len(self.output_blocks)):
+            skip = hs[len(hs) - 1 - i]
+            sc = control.pop() if (control is not None and not only_mid_control) else None
+            ops.add_rows(skip, sc, cats[i][..., cats[i].shape[-1] - skip.shape[-1]:])
+        return self.decode_cl(cats, ctx, out_dtype)
+
+    def encode_cl(self, x_cl, timesteps, context, img_control, only_mid_control: bool, cfg_dedup: bool):
+        """Input blocks + middle block.  Returns (hs: 12 skip tensors [B, T, h_l, w_l, C_l], h: middle output, ctx).  With
+        cfg_dedup hs[0] (the output of input block 0, ahead of the fan-out) has B entries, everything else 2 B."""
         dev = x_cl.device
         B, T, H, W, _ = x_cl.shape
         ctx = self._prepare_ctx(timesteps, context, 2 * B if cfg_dedup else B, T, dev)
-        control = None if control is None else list(control)
         img_control = None if img_control is None else list(img_control)
         mc = self.model_channels
         hs = []
@@ -425,38 +461,63 @@ class ControlledUNetModel3DTV2V(UNetModel):
                              res1=y4).view(B, T, H, W, mc)
             elif i == 1 and cfg_dedup:
                 h = module.run(h, ctx, dup=True)                    # [2B, T, H, W, C] from here on
-                B = 2 * B
                 if img_control is not None:
                     img_control = [ops.dup_rows(ic.contiguous()) for ic in img_control]
             else:
                 h = module.run(h, ctx)
             if img_control is not None and not only_mid_control:
                 ops.add_center_frame(h, img_control.pop(0))
-            hs.append(ops.dup_rows(h) if (i == 0 and cfg_dedup) else h)
+            hs.append(h)
         h = self.middle_block.run(h, ctx)
         if img_control is not None:
             ops.add_center_frame(h, img_control.pop(0))
-        # decoder: h = cat([h, hs.pop() + control.pop()], 1) -> module (controlmodel.py:536-544).  The concatenation is
-        # never a copy: the producer of h writes straight into channels [0, ch) of the next block's input buffer and
-        # the skip (+ control residual) is written into channels [ch, ch + cs).
-        mid_ctrl = control.pop() if control is not None else None
-        ch = h.shape[-1]
-        cat = torch.empty(*h.shape[:-1], ch + hs[-1].shape[-1], dtype=torch.float16, device=dev)
-        ops.add_rows(h, mid_ctrl, cat[..., :ch])                    # h = h + control.pop()
-        n_out = len(self.output_blocks)
+        return hs, h, ctx
+
+    def decoder_buffers(self, hs, h_mid) -> List[torch.Tensor]:
+        """The 12 concatenated decoder inputs cat([h, skip + control], 1) (controlmodel.py:541-543), allocated up front:
+        cats[i] = [B, T, h_i, w_i, Ch_i + Cs_i] is the input of output block i; its first Ch_i channels are written by the
+        producer of h (the previous output block, or middle + control for i = 0), the last Cs_i by whoever adds skip and
+        ControlNet residual (ops.add_rows, or the ControlNet's zero-conv GEMM itself: ControlNet2D.forward_cl(sinks=))."""
+        cats = []
+        B, T = h_mid.shape[0], h_mid.shape[1]
+        ch, hh, ww = h_mid.shape[-1], h_mid.shape[2], h_mid.shape[3]
         for i, module in enumerate(self.output_blocks):
-            skip = hs.pop()
-            ch = cat.shape[-1] - skip.shape[-1]
-            sc = control.pop() if (control is not None and not only_mid_control) else None
-            ops.add_rows(skip, sc, cat[..., ch:])
-            if i + 1 < n_out:
-                co = module.out_channels
-                nh, nw = (2 * cat.shape[2], 2 * cat.shape[3]) if module.upsamples else (cat.shape[2], cat.shape[3])
-                nxt = torch.empty(B, T, nh, nw, co + hs[-1].shape[-1], dtype=torch.float16, device=dev)
-                module.run(cat, ctx, out=nxt[..., :co])
-                cat = nxt
+            cs = hs[len(hs) - 1 - i].shape[-1]
+            cats.append(torch.empty(B, T, hh, ww, ch + cs, dtype=torch.float16, device=h_mid.device))
+            ch = module.out_channels
+            if module.upsamples:
+                hh, ww = 2 * hh, 2 * ww
+        return cats
+
+    def control_sinks(self, hs, h_mid, cats):
+        """(destination, residual) per ControlNet output, in the ControlNet's order (12 zero convs, then middle_block_out):
+        zero conv j lands in the skip half of cats[11 - j] on top of hs[j]; the middle one in the h half of cats[0] on top of
+        the middle block's output.  With a de-duplicated hs[0] (B entries against 2 B in cats[11]) the first sink is a pair."""
+        n = len(hs)
+        sinks = []
+        for j in range(n):
+            cat = cats[n - 1 - j]
+            dst = cat[..., cat.shape[-1] - hs[j].shape[-1]:]
+            if hs[j].shape[0] != cat.shape[0]:                      # fan-out of the shared block-0 output
+                Bh = hs[j].shape[0]
+                sinks.append([(dst[:Bh], hs[j]), (dst[Bh:], hs[j])])
             else:
-                h = module.run(cat, ctx)
+                sinks.append([(dst, hs[j])])
+        sinks.append([(cats[0][..., :h_mid.shape[-1]], h_mid)])
+        return sinks
+
+    def decode_cl(self, cats, ctx, out_dtype) -> torch.Tensor:
+        """Output blocks on the filled concat buffers + out head.  The concatenation is never a copy: every block writes
+        its result straight into channels [0, Ch) of the next block's input buffer."""
+        dev = cats[0].device
+        B, T = cats[0].shape[0], cats[0].shape[1]
+        n_out = len(self.output_blocks)
+        h = None
+        for i, module in enumerate(self.output_blocks):
+            if i + 1 < n_out:
+                module.run(cats[i], ctx, out=cats[i + 1][..., :module.out_channels])
+            else:
+                h = module.run(cats[i], ctx)
         # out: GN + SiLU + conv3x3 then y + conv1d_k3(SiLU(y)) over T (openaimodel.py:1513-1519, 1627-1632)
         Hh, Ww = h.shape[2], h.shape[3]
         a = ops.groupnorm_spatial(h.view(B * T, Hh, Ww, h.shape[-1]), *self.out["0"].affine(dev), GN_EPS_RES, True)

@@ -50,7 +50,6 @@ struct FaTcParams {
   int lq, d;
   float scale_log2;
   int hpc;            // heads per CTA (> 1 for short key sequences: amortises the CTA set-up, overlaps the next Q load)
-  int dev;            // developer switches (CCEDIT_ATTN_DEV): 1 = folded kernel without the lo query block, 2 = without barrier probes
   long long* trace;   // diagnostics (ccedit_gemm_trace): per-tile phase clocks of CTA 0, or nullptr
 };
 
@@ -390,6 +389,10 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         }
       }
     };
+    // An mbarrier wait costs ~100-200 clocks even when its phase completed long ago (TRYWAIT latency).  S(it + 1) and
+    // P.V(it - 1) are therefore probed with non-blocking tests issued under other work (the last P stores of a tile /
+    // the row maximum) and the blocking wait is only the fallback.
+    bool s_ready = false;
     for (int it = 0; it < total; ++it) {
       const int hl = MH ? it / ntiles : 0, j = it - hl * ntiles;   // head (local), key tile
       const int head = head0 + hl;
@@ -400,7 +403,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       }
       const int seg = j < p.ntile[0] ? 0 : 1;
       const int valid = p.lkv[seg] - (seg == 0 ? j : j - p.ntile[0]) * KT - HK * half;   // my keys that exist
-      mbar_wait(s_full, static_cast<uint32_t>(it & 1));
+      if (!s_ready) mbar_wait(s_full, static_cast<uint32_t>(it & 1));
       tcgen05_fence_after();
       uint32_t r[HK];
 #pragma unroll
@@ -408,6 +411,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(s_free);
+      const bool o_ready = it > 0 && mbar_test_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
       if (MH && half == 0 && last_tile && hl + 1 < hpc) q_issue(head + 1);   // Q of the next head (this head's QK^T are done)
       if (valid < HK) {
 #pragma unroll
@@ -435,7 +439,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       }
       bool owait = it > 0;                               // P / O still belong to P.V of the previous tile
       if (j > 0 && __any_sync(0xffffffffu, need)) {       // rare after the first tiles; the 16-column chunks alternate
-        mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
+        if (!o_ready) mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
         tcgen05_fence_after();
         owait = false;
 #pragma unroll 1
@@ -471,13 +475,14 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         }
         const bool alt = kPx && half == 0 && cc == 0;     // the first 32 keys of P have a second buffer (odd tiles)
         if (owait && !alt) {
-          mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
+          if (!o_ready) mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
           tcgen05_fence_after();
           owait = false;
         }
         tmem_st_x16(((alt && (it & 1)) ? tPx : tP) + (cc >> 1), pk);
       }
       l += (s0 + s1) + (s2 + s3);
+      s_ready = it + 1 < total && mbar_test_wait(s_full, static_cast<uint32_t>((it + 1) & 1));
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(p_full);
@@ -489,369 +494,6 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       }
     }
     if (!MH) head_epilogue(total - 1, head0, l);
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// "Folded" variant for head dims with a spare operand channel (d = 40 inside the 48-channel / 3 k-step operand: the L0
-// self-attention, 6144 keys, 78 % of the attention time of a network call).  The kernel above is co-limited by the MUFU
-// pipe and by instruction issue (ncu: XU 53 %, issue 71 %): per score it issues FFMA (scale, subtract the row reference),
-// MUFU.EX2 or its FMA-pipe polynomial, FADD (row sum), half an F2FP pack and half a max.  Here the tensor core does the
-// FFMA and the FADD:
-//   * Q is written to shared memory pre-multiplied by scale * log2(e), and the spare channel d carries -mref (the row's
-//     reference maximum, kept fp16-representable so that the product is exact) against a column of ones patched into
-//     the K tile: the accumulator IS x = scale*log2e*q.k - mref, ready for exp2;
-//   * a column of ones patched into the V tile makes column d of O the row sum of the fp16-rounded P - the normaliser
-//     matches the probabilities that were actually multiplied with V.
-// What is left per score: the exponential, half a pack, half a max: ~3.5 issue slots instead of ~6.
-// mref changes lazily (only when a row's maximum grows by more than 2^8), so the value baked into S is almost always
-// current; a thread whose row is stale (the first two key tiles, or after a rescale) adds the difference per element.
-// The cross-half exchange of the row maxima is speculative: every half publishes its maximum, computes P under the
-// assumption that no rescale is needed, and only then looks at the other half's value (named barriers used as
-// arrive / wait pairs: the other half's arrival is long past), recomputing the tile in the rare case the row reference
-// moved.  The ones columns are patched by the MMA-issuing warp right after the TMA of a stage has landed.
-// ---------------------------------------------------------------------------------------------------------------
-template <int KSTEPS, int EMU>
-__global__ void __launch_bounds__(kT2Threads, 2)
-flash_attn_fold_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
-                       const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
-                       const __grid_constant__ FaTcParams p) {
-  using Cfg = T2Cfg<KSTEPS>;
-  static_assert(Cfg::NB == 1, "folded variant: one 64-channel operand block");
-  constexpr int KT = Cfg::KT, NO = Cfg::NO, HK = KT / 2;
-  constexpr bool kPx = Cfg::kPx;
-  extern __shared__ uint8_t fa_smem_raw[];
-  const uint32_t raw_addr = smem_u32(fa_smem_raw);
-  uint8_t* smem = fa_smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;                                    // [2][128][128 B]: hi and lo halves of scale*log2e*q (see q load)
-  uint8_t* sKV = smem + 2 * Cfg::QBytes;                 // stages x (K [KT][128 B], V [KT][128 B])
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kT2Stages * 2 * Cfg::KBytes);
-  uint64_t* kv_full = bars;
-  uint64_t* kv_empty = bars + kT2Stages;
-  uint64_t* s_full = bars + 2 * kT2Stages;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* q_full = p_full + 1;
-  uint64_t* s_free = q_full + 1;
-  uint64_t* o_done = s_free + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
-  float* smax = reinterpret_cast<float*>(bars + 16);     // [2 parities][2 halves][128 rows]
-  float* lsum = smax + 512;                              // [128 rows]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTcTile, head = blockIdx.y, f = blockIdx.z;
-  const int d = p.d;                                     // d < 16 * KSTEPS: channel d is the spare one
-  const int total = p.ntile[0] + p.ntile[1];
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmK0);
-    tma_prefetch_desc(&tmV0);
-    for (int s = 0; s < kT2Stages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
-    mbar_init(q_full, 128);
-    mbar_init(s_free, 256);
-    mbar_init(o_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < total; ++it) {
-      const int seg = it < p.ntile[0] ? 0 : 1;
-      const int k0 = (seg == 0 ? it : it - p.ntile[0]) * KT;
-      const int kvf = (f / p.kv_div[seg]) * p.kv_mul[seg] + p.kv_add[seg];
-      mbar_wait(&kv_empty[stage], phase ^ 1u);
-      uint8_t* sK = sKV + stage * 2 * Cfg::KBytes;
-      mbar_arrive_expect_tx_warp(&kv_full[stage], 2u * Cfg::KBytes);
-      tma_load_3d_warp(sK, seg == 0 ? &tmK0 : &tmK1, &kv_full[stage], head * d, k0, kvf);
-      tma_load_3d_warp(sK + Cfg::KBytes, seg == 0 ? &tmV0 : &tmV1, &kv_full[stage], head * d, k0, kvf);
-      if (++stage == kT2Stages) {
-        stage = 0;
-        phase ^= 1u;
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (+ the ones columns of K and V) =====================
-    const uint32_t idesc_s = umma_idesc_f16(128, KT);
-    const uint32_t idesc_o = umma_idesc_f16(128, NO) | (1u << 16);       // B (= V) is MN-major
-    const uint32_t tS = tmem_base + Cfg::ColS, tO = tmem_base + Cfg::ColO, tP = tmem_base + Cfg::ColP, tPx = tmem_base + Cfg::ColX;
-    const uint32_t sQa = smem_u32(sQ);
-    // channel d of key row r sits in 16-byte chunk (d / 8) ^ (r & 7) of the row (SWIZZLE_128B), element d % 8
-    auto patch_ones = [&](int stage) {
-      uint8_t* sK = sKV + stage * 2 * Cfg::KBytes;
-#pragma unroll
-      for (int k = 0; k < KT / 32; ++k) {
-        const int r = lane + 32 * k;
-        const uint32_t off = static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(((d >> 3) ^ (r & 7))) << 4) +
-                             static_cast<uint32_t>(d & 7) * 2u;
-        *reinterpret_cast<uint16_t*>(sK + off) = 0x3C00u;                   // 1.0 (fp16)
-        *reinterpret_cast<uint16_t*>(sK + Cfg::KBytes + off) = 0x3C00u;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-    };
-    mbar_wait(&kv_full[0], 0);
-    patch_ones(0);
-    mbar_wait(q_full, 0);
-    fence_proxy_async_smem();
-    tcgen05_fence_after();
-    {
-      const uint32_t sKa = smem_u32(sKV);
-#pragma unroll
-      for (int ks = 0; ks < 2 * KSTEPS; ++ks)            // S = Qhi K^T + Qlo K^T: both Q blocks against the same K tile
-        if (ks < KSTEPS || !(p.dev & 1)) umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa + (ks >= KSTEPS ? Cfg::QBytes : 0)) + 2u * (ks % KSTEPS),
-                         umma_desc_k_sw128(sKa) + 2u * (ks % KSTEPS), idesc_s, ks ? 1u : 0u);
-      umma_commit_warp(s_full);
-    }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < total; ++it) {
-      int nstage = stage + 1;
-      uint32_t nphase = phase;
-      if (nstage == kT2Stages) {
-        nstage = 0;
-        nphase ^= 1u;
-      }
-      if (it + 1 < total) {                              // S(it+1) = Q K^T: S is free once it sits in registers
-        mbar_wait(&kv_full[nstage], nphase);
-        patch_ones(nstage);
-        mbar_wait(s_free, static_cast<uint32_t>(it & 1));
-        fence_proxy_async_smem();                        // the softmax threads may have rewritten the -mref channel of Q
-        tcgen05_fence_after();
-        const uint32_t sKa = smem_u32(sKV + nstage * 2 * Cfg::KBytes);
-#pragma unroll
-        for (int ks = 0; ks < 2 * KSTEPS; ++ks)
-          if (ks < KSTEPS || !(p.dev & 1)) umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa + (ks >= KSTEPS ? Cfg::QBytes : 0)) + 2u * (ks % KSTEPS),
-                           umma_desc_k_sw128(sKa) + 2u * (ks % KSTEPS), idesc_s, ks ? 1u : 0u);
-        umma_commit_warp(s_full);
-      }
-      const uint64_t dV = umma_desc_mn_sw128(smem_u32(sKV + stage * 2 * Cfg::KBytes + Cfg::KBytes), KT * 128);
-      mbar_wait(p_full, static_cast<uint32_t>(it & 1));
-      tcgen05_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < KT / 16; ++kk)
-        umma_f16_ts_warp(tO, ((kPx && kk < 2 && (it & 1)) ? tPx : tP) + 8u * kk, dV + 128u * kk, idesc_o, (it | kk) ? 1u : 0u);
-      umma_commit_warp(o_done);
-      umma_commit_warp(&kv_empty[stage]);
-      stage = nstage;
-      phase = nphase;
-    }
-  } else {
-    // ===================== softmax: warps 2-5 first half of the tile's keys, warps 6-9 second half =====================
-    const int half = (warp - 2) >> 2;
-    const int wq = warp & 3;
-    const int row = wq * 32 + lane;
-    const float c = p.scale_log2;
-    uint8_t* qrow_smem = sQ + row * 128;
-    const int sw = row & 7;
-    // the -mref slot of this thread's query row (channel d)
-    uint16_t* qm = reinterpret_cast<uint16_t*>(qrow_smem + ((((d >> 3) ^ sw)) << 4) + (d & 7) * 2);
-    if (half == 0) {
-      // Q row -> registers -> * scale*log2(e) -> fp16 hi + fp16 lo (the rounding residual of hi: the scaled query keeps
-      // ~22 significant bits, as accurate as scaling the fp32 scores) -> two swizzled operand blocks in shared memory;
-      // channels >= d zero (-mref = 0 to begin with)
-      const int chunks = d >> 3;
-      const int qrow = q0 + row;
-      const bool ok = qrow < p.lq;
-      const __half* src = p.q + static_cast<long long>(f) * p.q_fs + static_cast<long long>(ok ? qrow : 0) * p.ldq +
-                          static_cast<long long>(head) * d;
-#pragma unroll 1
-      for (int ch = 0; ch < 2 * KSTEPS; ++ch) {
-        uint4 u = make_uint4(0, 0, 0, 0), ul = make_uint4(0, 0, 0, 0);
-        if (ch < chunks && ok) {
-          u = __ldg(reinterpret_cast<const uint4*>(src) + ch);
-          uint32_t w[4] = {u.x, u.y, u.z, u.w}, wl[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-            const float px = v.x * c, py = v.y * c;
-            const __half2 hi = __floats2half2_rn(px, py);
-            const float2 hf = __half22float2(hi);
-            w[j] = *reinterpret_cast<const uint32_t*>(&hi);
-            wl[j] = pack_h2(px - hf.x, py - hf.y);
-          }
-          u = make_uint4(w[0], w[1], w[2], w[3]);
-          ul = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-        }
-        *reinterpret_cast<uint4*>(qrow_smem + (((ch & 7) ^ sw) << 4)) = u;
-        *reinterpret_cast<uint4*>(qrow_smem + Cfg::QBytes + (((ch & 7) ^ sw) << 4)) = ul;
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(q_full);
-    }
-    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + Cfg::ColS + static_cast<uint32_t>(HK * half);
-    const uint32_t tO = tmem_base + lane_off + Cfg::ColO;
-    const uint32_t tP = tmem_base + lane_off + Cfg::ColP + static_cast<uint32_t>((HK / 2) * half);
-    const uint32_t tPx = tmem_base + lane_off + Cfg::ColX;
-    // named barriers: 1 + parity (half 0 arrives, half 1 waits), 3 + parity (half 1 arrives, half 0 waits), 5: epilogue
-    float mref = -INFINITY;            // row reference (fp16-representable once set); identical in both halves
-    float mq = 0.f;                    // value the -mref channel of Q currently encodes (as +mref)
-    float mb_next = 0.f;               // reference baked into S(it + 1)
-    bool s_ready = false;              // S(it) was already seen complete by the probe at the end of the previous tile
-    for (int it = 0; it < total; ++it) {
-      const int par = it & 1;
-      const int seg = it < p.ntile[0] ? 0 : 1;
-      const int valid = p.lkv[seg] - (seg == 0 ? it : it - p.ntile[0]) * KT - HK * half;
-      // an mbarrier wait costs ~100-200 clocks even when its phase completed long ago (TRYWAIT latency): S(it) is probed
-      // with a non-blocking test issued under the previous tile's last stores, the blocking wait is the fallback
-      if (!s_ready) mbar_wait(s_full, static_cast<uint32_t>(par));
-      tcgen05_fence_after();
-      const float mb = mb_next;                          // reference baked into this tile's scores
-      if (mref != mq && mref != -INFINITY) {             // S(it) has been computed: Q may change for S(it + 1)
-        if (half == 0) {
-          *qm = __half_as_ushort(__float2half_rn(-mref));
-          fence_proxy_async_smem();
-        }
-        mq = mref;
-      }
-      mb_next = mq;
-      uint32_t r[HK];
-#pragma unroll
-      for (int cc = 0; cc < HK; cc += 32) tmem_ld_32x32b_x32(tS + cc, r + cc);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive(s_free);
-      if (valid < HK) {
-#pragma unroll
-        for (int i = 0; i < HK; ++i)
-          if (i >= valid) r[i] = 0xff800000u;            // -inf
-      }
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < HK; i += 8) {
-        m0 = max3_f(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        m1 = max3_f(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-        m2 = max3_f(m2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-        m3 = max3_f(m3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
-      }
-      const float mloc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) + mb;     // maximum of scale*log2e*q.k over my keys
-      float* sm = smax + par * 256 + row;
-      sm[half * 128] = mloc;
-      named_bar_arrive(1 + 2 * half + par, 256);          // published; nobody waits here
-      bool owait = it > 0;                               // P / O still belong to P.V of the previous tile
-      // same trick for P.V(it - 1): probe now, consume the answer at the first P store that needs it
-      const bool o_ready = it > 0 && !(p.dev & 2) && mbar_test_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
-      // ---- P from the scores: x = r + delta, delta = 0 when the baked reference is current ----
-      auto emit_p = [&](float delta, bool shifted) {
-#pragma unroll
-        for (int cc = 0; cc < HK; cc += 32) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float x0 = __uint_as_float(r[cc + i]), x1 = __uint_as_float(r[cc + i + 1]);
-            float x2 = __uint_as_float(r[cc + i + 2]), x3 = __uint_as_float(r[cc + i + 3]);
-            if (shifted) {
-              x0 += delta;
-              x1 += delta;
-              x2 += delta;
-              x3 += delta;
-            }
-            const float p0 = ex2_approx(x0);
-            const float p1 = ex2_approx(x1);
-            const float p2 = EMU >= 2 ? ex2_poly(x2) : ex2_approx(x2);
-            const float p3 = EMU >= 1 ? ex2_poly(x3) : ex2_approx(x3);
-            pk[i >> 1] = pack_h2(p0, p1);
-            pk[(i >> 1) + 1] = pack_h2(p2, p3);
-          }
-          const bool alt = kPx && half == 0 && cc == 0;   // the first 32 keys of P have a second buffer (odd tiles)
-          if (owait && !alt) {
-            if (!o_ready) mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
-            tcgen05_fence_after();
-            owait = false;
-          }
-          tmem_st_x16(((alt && par) ? tPx : tP) + (cc >> 1), pk);
-        }
-      };
-      // speculate: my half's maximum does not move the reference and the baked reference is current
-      const bool spec = __all_sync(0xffffffffu, mb == mref && mloc <= mref + 8.f);
-      if (spec) emit_p(0.f, false);
-      named_bar_sync(3 - 2 * half + par, 256);            // the other half's maximum (published before its own exponentials)
-      const float mt = fmaxf(mloc, sm[(half ^ 1) * 128]);
-      const bool need = mt > mref + 8.f;                  // identical in both halves of the row
-      if (!spec || __any_sync(0xffffffffu, need)) {
-        float alpha = 1.f;
-        if (need) {
-          const float mnew = __half2float(__float2half_rn(mt));
-          alpha = ex2_approx(mref - mnew);
-          mref = mnew;
-        }
-        if (it > 0 && __any_sync(0xffffffffu, need)) {    // O (and the row sum in its column d) move to the new reference
-          if (owait) {
-            if (!o_ready) mbar_wait(o_done, static_cast<uint32_t>((it - 1) & 1));
-            tcgen05_fence_after();
-            owait = false;
-          }
-#pragma unroll 1
-          for (int cc = 16 * half; cc < NO; cc += 32) {
-            uint32_t o[16];
-            tmem_ld_x16(tO + cc, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x16(tO + cc, o);
-          }
-        }
-        emit_p(mb - mref, true);
-      }
-      s_ready = it + 1 < total && !(p.dev & 2) && mbar_test_wait(s_full, static_cast<uint32_t>(par ^ 1));   // S(it + 1), see the loop head
-      tmem_st_wait();
-      tcgen05_fence_before();
-      mbar_arrive(p_full);
-    }
-    // ---- epilogue: O[:, :d] / O[:, d] -> fp16 -> global, the 16-column chunks split between the halves ----
-    {
-      mbar_wait(o_done, static_cast<uint32_t>((total - 1) & 1));
-      tcgen05_fence_after();
-      uint32_t lbits;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(lbits) : "r"(tO + static_cast<uint32_t>(d)) : "memory");
-      tmem_ld_wait();
-      const float lt = __uint_as_float(lbits);            // column d of O: the row sum of P (ones column of V)
-      const int qrow = q0 + row;
-      const float inv = 1.f / lt;
-      __half* dst = p.o + static_cast<long long>(f) * p.o_fs + static_cast<long long>(qrow < p.lq ? qrow : 0) * p.ldo +
-                    static_cast<long long>(head) * d;
-#pragma unroll 1
-      for (int cc = 16 * half; cc < NO; cc += 32) {
-        uint32_t o[16];
-        tmem_ld_x16(tO + cc, o);
-        tmem_ld_wait();
-        if (qrow < p.lq) {
-#pragma unroll
-          for (int h8 = 0; h8 < 16; h8 += 8) {
-            if (cc + h8 < d) {
-              uint4 u;
-              u.x = pack_h2(__uint_as_float(o[h8]) * inv, __uint_as_float(o[h8 + 1]) * inv);
-              u.y = pack_h2(__uint_as_float(o[h8 + 2]) * inv, __uint_as_float(o[h8 + 3]) * inv);
-              u.z = pack_h2(__uint_as_float(o[h8 + 4]) * inv, __uint_as_float(o[h8 + 5]) * inv);
-              u.w = pack_h2(__uint_as_float(o[h8 + 6]) * inv, __uint_as_float(o[h8 + 7]) * inv);
-              *reinterpret_cast<uint4*>(dst + cc + h8) = u;
-            }
-          }
-        }
-      }
-    }
-    (void)lsum;
   }
 
   tcgen05_fence_before();
@@ -917,27 +559,6 @@ static int launch_tc2_t(const CUtensorMap* maps, const FaTcParams& p, int frames
 }
 
 template <int KSTEPS, int EMU>
-static int launch_fold(const CUtensorMap* maps, const FaTcParams& p, int frames, int heads, cudaStream_t st) {
-  const int smem = T2Cfg<KSTEPS>::Smem + T2Cfg<KSTEPS>::QBytes;      // second (lo) block of the scaled query
-  static std::atomic<bool> attr_set[kMaxDevices];
-  const int dev = current_device();
-  CCEDIT_CHECK_ARG(dev >= 0, "ccedit_attention(fold): no current CUDA device");
-  if (!attr_set[dev].load(std::memory_order_acquire)) {
-    const cudaError_t e = cudaFuncSetAttribute(flash_attn_fold_kernel<KSTEPS, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) {
-      set_last_error("ccedit_attention(fold): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return CCEDIT_ERR_CUDA;
-    }
-    attr_set[dev].store(true, std::memory_order_release);
-  }
-  dim3 grid((p.lq + kTcTile - 1) / kTcTile, heads, frames);
-  flash_attn_fold_kernel<KSTEPS, EMU><<<grid, kT2Threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
-  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_attention(fold)");
-  return CCEDIT_OK;
-}
-
-template <int KSTEPS, int EMU>
 static int launch_tc2(const CUtensorMap* maps, const FaTcParams& p, int frames, int heads, cudaStream_t st) {
   return p.hpc > 1 ? launch_tc2_t<KSTEPS, EMU, true>(maps, p, frames, heads, st)
                    : launch_tc2_t<KSTEPS, EMU, false>(maps, p, frames, heads, st);
@@ -986,8 +607,6 @@ int attention_tc(const ccedit_attn_desc* a, cudaStream_t st) {
   p.d = a->d;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.trace = g_trace_buf;
-  static const int attn_dev = [] { const char* e = getenv("CCEDIT_ATTN_DEV"); return e ? atoi(e) : 0; }();
-  p.dev = attn_dev;
   // Heads per CTA: with one or two key tiles per head (text cross-attention: 77 keys) a CTA's life is all set-up
   // (TMEM allocation, barrier init, descriptor fetch, Q / K / V latency: ~6 us for ~1.5 us of work), so it takes several
   // heads in a row as long as enough CTAs remain to fill the 2 x 148 slots a few times over.
@@ -1012,15 +631,8 @@ int attention_tc(const ccedit_attn_desc* a, cudaStream_t st) {
   switch (ks) {
     case 1: return launch_tc2<1, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
     case 2: return launch_tc2<2, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
-    case 3: {
-      // d = 40 with many key tiles (the L0 self-attention / cross-frame attention): the folded kernel (spare channel 40)
-      static const int fold = [] { const char* e = getenv("CCEDIT_ATTN_FOLD"); return e ? atoi(e) : 1; }();
-      if (fold && a->d < 48 && p.hpc == 1 && p.ntile[0] + p.ntile[1] >= 3)
-        return emu == 0 ? launch_fold<3, 0>(maps, p, a->frames, a->heads, st)
-                        : launch_fold<3, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
-      return emu == 0 ? launch_tc2<3, 0>(maps, p, a->frames, a->heads, st)
-                      : launch_tc2<3, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
-    }
+    case 3: return emu == 0 ? launch_tc2<3, 0>(maps, p, a->frames, a->heads, st)
+                            : launch_tc2<3, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
     case 4: return launch_tc2<4, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
     case 5: return launch_tc2<5, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
     case 6: return launch_tc2<6, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);

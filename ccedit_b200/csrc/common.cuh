@@ -250,6 +250,36 @@ __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
+// ---- thread-block clusters: weight tiles are TMA-multicast to the CTAs of a cluster (tap_gemm_kernel<..., CL = 2>) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {       // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D tile load delivered to the same shared-memory offset (and signalling the same mbarrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_multicast_warp(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                           uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;\n\t}" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast_warp(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32b, 16 consecutive columns: thread i of the warp gets lane (base_lane+i), cols [c, c+16)

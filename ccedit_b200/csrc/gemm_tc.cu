@@ -41,6 +41,7 @@ struct GemmKParams {
   int tiles[4];
   int n_tiles;
   int total_tiles;
+  int total_pairs;    // CL = 2: ceil(m_tiles / 2) * n_tiles work items, each a pair of M-adjacent tiles sharing one W tile
   int ntaps;
   int kchunks;
   int bn;
@@ -140,9 +141,25 @@ __device__ __forceinline__ void add_res(float (&v)[16], const uint4 (&r)[2]) {
   }
 }
 
-template <int MODE, int NRES, bool LNF>
+// Tile sequence of a CTA.  CL = 1: tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n_tile fastest), advanced as mixed-radix
+// digits without divisions.  CL = 2 (cluster of two CTAs sharing every W tile by TMA multicast): the CLUSTER walks the
+// pair sequence cid, cid + nclusters, ...; pair (n_tile, mp) = M tiles 2 mp and 2 mp + 1 of the same N tile, this CTA takes
+// 2 mp + rank.  Digits are recomputed by division (long-K tiles only); an M tile past the end (odd tile count) has
+// dig[4] >= tiles[3]: all its rows are out of range, TMA zero-fills its loads and clips its stores.
+__device__ __forceinline__ void pair_digits(const GemmKParams& p, int pt, int crank, int (&dig)[5]) {
+  dig[0] = pt % p.n_tiles;
+  int m = 2 * (pt / p.n_tiles) + crank;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    dig[i + 1] = m % p.tiles[i];
+    m /= p.tiles[i];
+  }
+  dig[4] = m;
+}
+
+template <int MODE, int NRES, bool LNF, int CL>
 __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
-                                              uint64_t* tempty_bar, float* sbias_all, int warp, int lane) {
+                                              uint64_t* tempty_bar, float* sbias_all, int warp, int lane, int crank) {
   constexpr bool GEGLU = MODE == kModeGeglu;
   const int wq = warp & 3;            // TMEM lane quarter this warp may access
   const int eg = (warp - 2) >> 2;     // epilogue group: takes the 16-column chunks with (chunk index & 1) == eg
@@ -184,8 +201,12 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
   int titer = 0;
   int staged_ntile = -1;                // N tile whose bias row (and column sums) sit in sbias / scs
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  const int it0 = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int itstep = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int ittotal = CL == 2 ? p.total_pairs : p.total_tiles;
+  for (int tile = it0; tile < ittotal; tile += itstep) {
     if (tracing && titer < 64) p.trace[16 * titer + 0] = clock64();
+    if (CL == 2) pair_digits(p, tile, crank, dig);
     const int n_tile = dig[0];
     bool valid = true;
     long long off_o = lo_o, off_r1 = lo_r1, off_r2 = lo_r2;
@@ -357,12 +378,14 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
     as ^= 1;
     if (as == 0) aphase ^= 1u;
     // next tile: mixed-radix add with carry
-    int carry = 0;
+    if (CL == 1) {
+      int carry = 0;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      int d = dig[i] + inc[i] + carry;
-      carry = d >= radix[i] ? 1 : 0;
-      dig[i] = d - (carry ? radix[i] : 0);
+      for (int i = 0; i < 5; ++i) {
+        int d = dig[i] + inc[i] + carry;
+        carry = d >= radix[i] ? 1 : 0;
+        dig[i] = d - (carry ? radix[i] : 0);
+      }
     }
   }
 }
@@ -379,11 +402,11 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
 //   * the thread adds bias / time-embedding row / activation / residual to its TMEM row and overwrites the region in
 //     place; lane 0 stores the 32 x W box with one TMA store (rows past the end of the tensor are clipped by TMA).
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE, int NRES, bool LNF>
+template <int MODE, int NRES, bool LNF, int CL>
 __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmRes,
                                                 uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                                 uint64_t* res_bar_all, float* sbias_all, uint8_t* tbuf, int warp,
-                                                int lane) {
+                                                int lane, int crank) {
   constexpr bool GEGLU = MODE == kModeGeglu;
   const int wq = warp & 3;            // TMEM lane quarter this warp may access
   const int eg = (warp - 2) >> 2;     // column half of the tile
@@ -425,8 +448,12 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
       inc[i] = g % radix[i]; g /= radix[i];
     }
   }
+  const int it0 = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int itstep = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int ittotal = CL == 2 ? p.total_pairs : p.total_tiles;
+  if (CL == 2) pair_digits(p, it0, crank, dig);
   // residual of the first tile
-  if (NRES >= 1 && static_cast<int>(blockIdx.x) < p.total_tiles && lane == 0) {
+  if (NRES >= 1 && it0 < ittotal && lane == 0) {
     mbar_arrive_expect_tx(&rbar[0], static_cast<uint32_t>(32 * W * 2));
     for (int bk = 0; bk < nblk; ++bk)
       tma_load_5d(region0 + bk * blk_bytes, tmRes, &rbar[0], dig[0] * ncols_out + eg * W + bk * p.cb,
@@ -439,7 +466,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
   int staged_ntile = -1;                // N tile whose bias row (and column sums) sit in sbias / scs
   uint32_t aphase = 0, rph0 = 0, rph1 = 0;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+  for (int tile = it0; tile < ittotal; tile += itstep, ++it) {
     if (tracing && it < 64) p.trace[16 * it + 0] = clock64();
     const int b = (p.nbuf == 2) ? (it & 1) : 0;
     const int n_tile = dig[0];
@@ -476,7 +503,9 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
     const __half* r2ptr = p.res2 + off_r2 + col0_out;        // dereferenced only if NRES >= 2 and valid
     // next tile (mixed-radix add with carry)
     int ndig[5];
-    {
+    if (CL == 2) {
+      pair_digits(p, tile + itstep, crank, ndig);
+    } else {
       int carry = 0;
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
@@ -485,7 +514,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
         ndig[i] = d - (carry ? radix[i] : 0);
       }
     }
-    const bool has_next = tile + static_cast<int>(gridDim.x) < p.total_tiles;
+    const bool has_next = tile + itstep < ittotal;
 
     // ---- bias row of this warp's columns -> per-warp shared memory (GEGLU: W value columns, then W gate columns) ----
     uint4 c2[2], n2[2];
@@ -666,7 +695,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
   __syncwarp();
 }
 
-template <int MODE, int NRES, bool STAGED, bool LNF>
+template <int MODE, int NRES, bool STAGED, bool LNF, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -688,13 +717,18 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CL = 2: the two CTAs of a cluster work on M-adjacent tiles of the same N tile; each loads half of the W tile and
+  // multicasts it to both, so a W tile crosses the L2 -> SM path once per 256 rows instead of once per 128 (the big-K
+  // GEMMs run at the 64 B/clk/SM limit of that path).  A slot may be refilled once BOTH CTAs have consumed it: the MMA
+  // commits arrive on the `empty` barrier of both CTAs (count 2).
+  const int crank = CL == 2 ? static_cast<int>(cluster_ctarank()) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -713,22 +747,27 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();          // the peer's barriers are initialised before anything can arrive on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int kblocks = p.ntaps * p.kchunks;
+  const int it0 = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int itstep = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int ittotal = CL == 2 ? p.total_pairs : p.total_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int half_rows = p.bn >> 1;         // CL = 2: W rows this CTA fetches (and multicasts) per stage
+    for (int tile = it0; tile < ittotal; tile += itstep) {
       const int n_tile = tile % p.n_tiles;
-      int m = tile / p.n_tiles;
+      int m = CL == 2 ? 2 * (tile / p.n_tiles) + crank : tile / p.n_tiles;
       int o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        o[i] = (m % p.tiles[i]) * p.box[i];
+        o[i] = (i < 3 ? m % p.tiles[i] : m) * p.box[i];      // past-the-end M tiles (CL = 2, odd count): TMA zero fill
         m /= p.tiles[i];
       }
       for (int tap = 0; tap < p.ntaps; ++tap) {
@@ -739,7 +778,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* sa = smem + stage * stage_bytes;
           mbar_arrive_expect_tx_warp(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
           tma_load_5d_warp(sa, &tmA, &full_bar[stage], kc * kBlockK, c1, c2, c3, c4);
-          tma_load_2d_warp(sa + kABytes, &tmB, &full_bar[stage], (tap * p.kchunks + kc) * kBlockK, n_tile * p.bn);
+          if (CL == 2)
+            tma_load_2d_multicast_warp(sa + kABytes + crank * half_rows * 128, &tmB, &full_bar[stage],
+                                       (tap * p.kchunks + kc) * kBlockK, n_tile * p.bn + crank * half_rows, 3);
+          else
+            tma_load_2d_warp(sa + kABytes, &tmB, &full_bar[stage], (tap * p.kchunks + kc) * kBlockK, n_tile * p.bn);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -755,7 +798,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t aphase = 0;
     int mt = 0;
     const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = it0; tile < ittotal; tile += itstep) {
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
       tcgen05_fence_after();
       if (tr && mt < 64) p.trace[16 * mt + 5] = clock64();
@@ -772,7 +815,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in 16-byte units
           umma_f16_ss_warp(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit_warp(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        if (CL == 2) umma_commit_multicast_warp(&empty_bar[stage], 3);   // the slot is free in BOTH CTAs' books
+        else umma_commit_warp(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
@@ -787,13 +831,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // ===================== epilogue warps =====================
     if (STAGED)
-      epilogue_staged<MODE, NRES, LNF>(p, &tmOut, &tmRes, tmem_base, tfull_bar, tempty_bar, res_bar, sbias_all, tbuf, warp, lane);
+      epilogue_staged<MODE, NRES, LNF, CL>(p, &tmOut, &tmRes, tmem_base, tfull_bar, tempty_bar, res_bar, sbias_all, tbuf, warp,
+                                           lane, crank);
     else
-      epilogue_loop<MODE, NRES, LNF>(p, tmem_base, tfull_bar, tempty_bar, sbias_all, warp, lane);
+      epilogue_loop<MODE, NRES, LNF, CL>(p, tmem_base, tfull_bar, tempty_bar, sbias_all, warp, lane, crank);
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -838,26 +884,73 @@ int device_sm_count() {
 
 extern long long* g_trace_buf;
 
-template <int MODE, int NRES, bool STAGED, bool LNF>
-static cudaError_t launch_gemm_t(const CUtensorMap* tm, const GemmKParams& p, int grid, int smem_bytes,
+// Launch one instantiation; cl = 2 launches clusters of two CTAs (cudaLaunchAttributeClusterDimension).  Function
+// attributes and the cluster capacity belong to a device: cached per device ordinal.
+template <int MODE, int NRES, bool STAGED, bool LNF, int CL>
+static cudaError_t launch_gemm_t(const CUtensorMap* tm, const GemmKParams& p, int work_items, int smem_bytes,
                                  cudaStream_t stream) {
-  static std::atomic<bool> attr_set[kMaxDevices];
+  static std::atomic<int> cap[kMaxDevices];              // 0: not initialised; CTAs (CL = 1) / clusters (CL = 2) to launch at most
   const int dev = current_device();
   if (dev < 0) return cudaErrorInvalidDevice;
-  if (!attr_set[dev].load(std::memory_order_acquire)) {
-    const cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<MODE, NRES, STAGED, LNF>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  auto kern = tap_gemm_kernel<MODE, NRES, STAGED, LNF, CL>;
+  int capacity = cap[dev].load(std::memory_order_acquire);
+  if (capacity == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set[dev].store(true, std::memory_order_release);
+    const int sms = device_sm_count();
+    if (sms <= 0) return cudaErrorInvalidDevice;
+    capacity = sms;
+    if (CL == 2) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(2 * (sms / 2));
+      q.blockDim = dim3(kGemmThreads);
+      q.dynamicSmemBytes = 227 * 1024;
+      cudaLaunchAttribute a;
+      a.id = cudaLaunchAttributeClusterDimension;
+      a.val.clusterDim.x = 2;
+      a.val.clusterDim.y = 1;
+      a.val.clusterDim.z = 1;
+      q.attrs = &a;
+      q.numAttrs = 1;
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &q);
+      if (e != cudaSuccess) return e;
+      capacity = n < sms / 2 ? n : sms / 2;
+      if (capacity < 1) return cudaErrorLaunchOutOfResources;
+    }
+    cap[dev].store(capacity, std::memory_order_release);
   }
-  tap_gemm_kernel<MODE, NRES, STAGED, LNF><<<grid, kGemmThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
-  return cudaGetLastError();
+  const int units = work_items < capacity ? work_items : capacity;
+  if (CL == 1) {
+    kern<<<units, kGemmThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * units);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  void* args[] = {const_cast<CUtensorMap*>(&tm[0]), const_cast<CUtensorMap*>(&tm[1]), const_cast<CUtensorMap*>(&tm[2]),
+                  const_cast<CUtensorMap*>(&tm[3]), const_cast<GemmKParams*>(&p)};
+  return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), args);
 }
 template <int MODE, int NRES, bool LNF = false>
-static cudaError_t launch_gemm(const CUtensorMap* tm, const GemmKParams& p, bool staged, int grid, int smem_bytes,
+static cudaError_t launch_gemm(const CUtensorMap* tm, const GemmKParams& p, bool staged, int cl, int smem_bytes,
                                cudaStream_t stream) {
-  return staged ? launch_gemm_t<MODE, NRES, true, LNF>(tm, p, grid, smem_bytes, stream)
-                : launch_gemm_t<MODE, NRES, false, LNF>(tm, p, grid, smem_bytes, stream);
+  if (cl == 2)
+    return staged ? launch_gemm_t<MODE, NRES, true, LNF, 2>(tm, p, p.total_pairs, smem_bytes, stream)
+                  : launch_gemm_t<MODE, NRES, false, LNF, 2>(tm, p, p.total_pairs, smem_bytes, stream);
+  return staged ? launch_gemm_t<MODE, NRES, true, LNF, 1>(tm, p, p.total_tiles, smem_bytes, stream)
+                : launch_gemm_t<MODE, NRES, false, LNF, 1>(tm, p, p.total_tiles, smem_bytes, stream);
 }
 
 // Output-side tensor map of the staged epilogue: the [d4][d3][d2][d1][cols] view behind `base` with box
@@ -909,6 +1002,15 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     return CCEDIT_ERR_CUDA;
   }
 
+  // Clusters of two CTAs sharing the W tiles (TMA multicast): for the GEMMs whose K loop is long enough that the tile is
+  // paced by operand delivery over the L2 -> SM path (convolutions, temporal k3, K >= 640 linears) and that have at least
+  // one pair of M tiles per SM pair.  CCEDIT_GEMM_CLUSTER: 0 = never, 1 = default rule, 2 = wherever possible.
+  static const int cluster_mode = [] { const char* e = getenv("CCEDIT_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
+  long long m_tiles_all = 1;
+  for (int i = 0; i < 4; ++i) m_tiles_all *= (d->out_dims[i] + d->box[i] - 1) / d->box[i];
+  const int kblocks_all = d->ntaps * (d->kpad / kBlockK);
+  const int cl = (cluster_mode == 2 || (cluster_mode == 1 && kblocks_all >= 10)) && m_tiles_all >= 2 ? 2 : 1;
+
   CUtensorMap tm[4];
   CUtensorMap& tmA = tm[0];
   CUtensorMap& tmB = tm[1];
@@ -932,7 +1034,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->ntaps * d->kpad, (cuuint64_t)d->n};
     cuuint64_t strides[1] = {(cuuint64_t)d->ntaps * d->kpad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)d->bn};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(d->bn / cl)};   // cl = 2: each CTA fetches half of the W tile
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -958,6 +1060,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.n_tiles = d->n / d->bn;
   CCEDIT_CHECK_ARG(m_tiles * p.n_tiles < (1ll << 31), "ccedit_gemm: too many tiles");
   p.total_tiles = static_cast<int>(m_tiles * p.n_tiles);
+  p.total_pairs = static_cast<int>(((m_tiles + 1) / 2) * p.n_tiles);
   p.ntaps = d->ntaps;
   p.kchunks = d->kpad / kBlockK;
   p.bn = d->bn;
@@ -1042,14 +1145,9 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + (staged ? p.nbuf * p.tbuf_bytes : 0) + fixed_bytes;
 
-  const int sms = device_sm_count();
-  if (sms <= 0) {
-    set_last_error("ccedit_gemm: no CUDA device");
-    return CCEDIT_ERR_CUDA;
-  }
   // (A grid rounded down to a multiple of n_tiles would keep every CTA on one N tile and save the per-tile staging for
   //  N = 960 / 2560 as well; measured: the SMs given up cost more than the staging - GEGLU 367 -> 391 us.)
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const int grid = cl;                                   // launch_gemm sizes the grid: min(work items, SMs or cluster capacity)
   if (d->stats_out) {
     CCEDIT_CHECK_ARG(!geglu && !(d->flags & CCEDIT_GEMM_SILU) && d->out_dims[1] == 1 && d->out_dims[2] == 1 && d->out_dims[3] == 1,
                      "ccedit_gemm: stats_out needs a plain 2-D [M, C] GEMM");

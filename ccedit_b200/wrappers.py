@@ -47,16 +47,19 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
         x_cl = _to_cl(x, 8)                                                       # [B, T, h, w, 8]
         # hint: 1 - (hint + 1) / 2  (wrappers.py:160-162) folded into the layout change
         hint_cl = ops.ncthw_to_cl(control_hint, 8, pre=1.0, mul=-0.5, add=1.0)    # [B, T, 8h, 8w, 8]
-        control = net.controlnet.forward_cl(x_cl.view(B * T, h, w, 8),
-                                            hint_cl.view(B * T, hint_cl.shape[2], hint_cl.shape[3], 8), t, crossattn,
-                                            B, T)
         img_control = None
         if cond_feat is not None:
             feat_cl = _to_cl(cond_feat.unsqueeze(2), 8)                           # [B, 1, h, w, 8]
             # wrappers.py:180-186: controlnet_img sees the centre frame of x (ignored when it was built with no_add_x)
             xc_cl = None if net.controlnet_img.no_add_x else x_cl[:, T // 2].contiguous()
             img_control = net.controlnet_img.forward_cl(xc_cl, feat_cl.view(B, h, w, 8), t, crossattn, B, 1)
-        return net.forward_cl(x_cl, t, crossattn, control, img_control, False, x.dtype)
+        # UNet encoder first, then the ControlNet: its zero convs add their residual to the encoder's skips and write the
+        # sums straight into the decoder's concat buffers (controlmodel.py:536-543 without the 13 control tensors)
+        hs, hm, ctx = net.encode_cl(x_cl, t, crossattn, img_control, False, False)
+        cats = net.decoder_buffers(hs, hm)
+        net.controlnet.forward_cl(x_cl.view(B * T, h, w, 8), hint_cl.view(B * T, hint_cl.shape[2], hint_cl.shape[3], 8),
+                                  t, crossattn, B, T, sinks=net.control_sinks(hs, hm, cats))
+        return net.decode_cl(cats, ctx, x.dtype)
 
     def forward_cfg(self, x: torch.Tensor, t: torch.Tensor, c: dict) -> torch.Tensor:
         """One network call for a classifier-free-guidance batch whose two halves share everything but the text:
@@ -78,9 +81,6 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
             t2 = torch.cat([t] * 2)
             x_cl = _to_cl(x, 8)
             hint_cl = ops.ncthw_to_cl(hint, 8, pre=1.0, mul=-0.5, add=1.0)
-            control = net.controlnet.forward_cl(x_cl.view(B * T, h, w, 8),
-                                                hint_cl.view(B * T, hint_cl.shape[2], hint_cl.shape[3], 8), t2, crossattn,
-                                                2 * B, T, cfg_dedup=True)
             img_control = None
             if feat is not None:
                 if not net.controlnet_img.disable_text_ca:
@@ -89,7 +89,11 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
                 feat_cl = _to_cl(feat[:B].unsqueeze(2), 8)
                 xc_cl = None if net.controlnet_img.no_add_x else x_cl[:, T // 2].contiguous()
                 img_control = net.controlnet_img.forward_cl(xc_cl, feat_cl.view(B, h, w, 8), t, None, B, 1)
-            return net.forward_cl(x_cl, t2, crossattn, control, img_control, False, x.dtype, cfg_dedup=True)
+            hs, hm, ctx = net.encode_cl(x_cl, t2, crossattn, img_control, False, True)
+            cats = net.decoder_buffers(hs, hm)
+            net.controlnet.forward_cl(x_cl.view(B * T, h, w, 8), hint_cl.view(B * T, hint_cl.shape[2], hint_cl.shape[3], 8),
+                                      t2, crossattn, 2 * B, T, cfg_dedup=True, sinks=net.control_sinks(hs, hm, cats))
+            return net.decode_cl(cats, ctx, x.dtype)
 
     def _graphed(self, x, t, crossattn, control_hint, cond_feat):
         ins = dict(x=x, t=t, crossattn=crossattn, control_hint=control_hint, cond_feat=cond_feat)

@@ -45,7 +45,10 @@ def test_public_forward_chain_equals_wrapper(kind, gpu_wrappers):
                   only_mid_control=False)
     assert control == [] and (img_control is None or img_control == [])            # consumed like control.pop()
     assert out.dtype == x.dtype and out.is_contiguous()
-    assert torch.equal(out, fast)                                                   # same kernels, same order: bit-equal
+    # Same kernels on the same data up to one point: the public path materialises the 13 control tensors in fp16 and adds
+    # them to the skips afterwards (two roundings), the wrapper's fast path adds the skip inside the zero conv's fp32
+    # epilogue (one rounding).  The difference is a few fp16 ulps on 13 tensors.
+    assert rel_err(out, fast) < 5e-4
     assert rel_err(out, g["output"]) < NET_TOL
 
 

@@ -74,4 +74,4 @@ def test_decode_headline_size_properties(vae):
     assert tuple(out.shape) == (1, 3, 17, 512, 768) and torch.isfinite(out).all()
     assert torch.equal(vae.decode(z, scale=1.0 / 0.18215), out)
     one = vae.decode(z[:, :, 5:6], scale=1.0 / 0.18215)
-    assert rel_err(one, out[:, :, 5:6]) < 1e-3
+    assert rel_err(one, out[:, :, 5:6]) < VAE_TOL      # GroupNorm slicing (summation order) depends on the frame count

@@ -104,6 +104,43 @@ def main():
         del wrap
         torch.cuda.empty_cache()
 
+    # ---- sampler (3 DPM++2S-ancestral steps, CFG 7.5, 5 network calls) through the fused step ----
+    from ccedit_b200.sampling import BoundDenoiser, DiscreteDenoiser, FusedDPMPP2SAncestralSampler
+    sd = seeded_state_dict(load_manifest("tv2v"), seed=0)
+    wrap = build_network("tv2v", device="cpu", use_cuda_graph=False)
+    wrap.load_state_dict(sd, strict=True)
+    wrap = wrap.cuda()
+    g = load_golden("sampler_tv2v.pt")
+    B, T, h, w = g["shape"]
+    c, uc = oin.synthetic_cond(B, T, h, w, seed=7)
+    x0 = oin.synthetic_latent(B, T, h, w, seed=6)
+    gn = torch.Generator().manual_seed(8)
+    noises = iter([torch.randn(x0.shape, generator=gn).cuda() for _ in range(g["steps"])])
+    sampler = FusedDPMPP2SAncestralSampler(num_steps=g["steps"], device="cuda", eta=1.0, s_noise=1.0, guider_config={
+        "target": "sgm.modules.diffusionmodules.guiders.VanillaCFGTV2V", "params": {"scale": g["scale"]}})
+    sampler.noise_sampler = lambda x: next(noises)
+    cu = lambda d: {k: v.cuda() for k, v in d.items()}
+    out = sampler(BoundDenoiser(DiscreteDenoiser().cuda(), wrap), x0.clone().cuda(), cu(c), uc=cu(uc))
+    row("tv2v/sampler 3 steps, cfg 7.5 (fused step, CFG de-duplication)", out, g["output"])
+    del wrap
+    torch.cuda.empty_cache()
+
+    # ---- first stage (reference runs it in fp32: the floor columns do not apply) ----
+    from oracle.vae_oracle import DDCONFIG, SCALE_FACTOR
+    from ccedit_b200.autoencoder import AutoencoderKLInferenceWrapper
+    import test_vae_gpu as tv
+    vae = AutoencoderKLInferenceWrapper(ddconfig=dict(DDCONFIG), embed_dim=4)
+    vae.load_state_dict(seeded_state_dict(load_manifest("vae"), seed=0), strict=True)
+    vae = vae.cuda().eval()
+    gold = load_golden("vae.pt")
+    with torch.no_grad():
+        for name in ("res_512", "res_256_128", "attn_512", "attn_512_big", "up_512", "down_128"):
+            gg = gold[name]
+            row(f"vae/{name}", tv._mod(vae, gg["prefix"]).run(tv._cl(gg["inputs"][0])).permute(0, 3, 1, 2), gg["output"])
+        for name in ("decode_video", "decode_frame"):
+            row(f"vae/{name}", vae.decode(gold[name]["inputs"][0].cuda(), scale=1.0 / SCALE_FACTOR), gold[name]["output"])
+        row("vae/encode_moments", vae.encode_moments(gold["encode_moments"]["inputs"][0].cuda()), gold["encode_moments"]["output"])
+
 
 if __name__ == "__main__":
     main()
