@@ -202,14 +202,16 @@ extern "C" int ccedit_hint_stem01(const void* x, void* y, const void* w0, const 
   CCEDIT_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(w0) & 3) == 0 && (reinterpret_cast<uintptr_t>(w1) & 3) == 0,
                    "ccedit_hint_stem01: x/y must be 16-byte aligned, w0/w1 4-byte aligned");
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(hint_stem01_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHsSmem);
-  });
-  if (attr_err != cudaSuccess) {
-    set_last_error("ccedit_hint_stem01: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    return CCEDIT_ERR_CUDA;
+  static std::atomic<bool> attr_set[kMaxDevices];         // function attributes belong to a device
+  const int dev = current_device();
+  CCEDIT_CHECK_ARG(dev >= 0, "ccedit_hint_stem01: no current CUDA device");
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    const cudaError_t e = cudaFuncSetAttribute(hint_stem01_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHsSmem);
+    if (e != cudaSuccess) {
+      set_last_error("ccedit_hint_stem01: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CCEDIT_ERR_CUDA;
+    }
+    attr_set[dev].store(true, std::memory_order_release);
   }
   dim3 grid((W + kHsTW - 1) / kHsTW, (H + kHsTH - 1) / kHsTH, F);
   hint_stem01_kernel<<<grid, kHsThreads, kHsSmem, static_cast<cudaStream_t>(stream)>>>(
