@@ -372,10 +372,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
     if (tracing && titer < 64) p.trace[16 * titer + 3] = clock64();
     tcgen05_fence_before();
     __syncwarp();
-    if (lane == 0) {                    // CL = 2: the accumulators of BOTH CTAs are released on the leader's barrier
-      if (CL == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
-      else mbar_arrive(&tempty_bar[as]);
-    }
+    if (lane == 0) mbar_arrive(&tempty_bar[as]);
     if (tracing && titer < 64) p.trace[16 * titer + 4] = clock64();
     ++titer;
     as ^= 1;
@@ -673,8 +670,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
     fence_proxy_async_smem();                                // this thread's staging writes -> visible to the TMA store
     __syncwarp();
     if (lane == 0) {
-      if (CL == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
-      else mbar_arrive(&tempty_bar[as]);
+      mbar_arrive(&tempty_bar[as]);
       for (int bk = 0; bk < nblk; ++bk)
         tma_store_5d(tmOut, region + bk * blk_bytes, n_tile * ncols_out + eg * W + bk * p.cb, dig[1] * p.box[0] + qoff[0],
                      dig[2] * p.box[1] + qoff[1], dig[3] * p.box[2] + qoff[2], dig[4] * p.box[3] + qoff[3]);
@@ -708,7 +704,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // SWIZZLE_128B wants 1024 B alignment
 
-  const int stage_bytes = kABytes + (CL == 2 ? p.bn / 2 : p.bn) * kBlockK * 2;   // CL = 2: this CTA holds half of the W tile
+  const int stage_bytes = kABytes + p.bn * kBlockK * 2;
   // [stages x (A, B)] [STAGED: nbuf tile buffers] [barriers, 512 B] [per-warp bias rows]; every part a multiple of 1 KiB
   uint8_t* tbuf = smem + p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tbuf + (STAGED ? p.nbuf * p.tbuf_bytes : 0));
@@ -721,26 +717,22 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // CL = 2: a CTA pair (cluster of two, tcgen05 cta_group::2) computes a 256 x BN tile: M-adjacent 128-row tiles of the
-  // same N tile.  Each CTA loads its own A tile and HALF of the W tile; the leader (rank 0) issues one MMA per k-step that
-  // drives the tensor cores of both SMs, each reading its A rows from its own shared memory and the W rows from both.
-  // Per MMA a CTA's shared memory delivers 4 KB of A + BN/2 rows of W instead of BN rows (the M = 128 kernel at BN = 160
-  // needs 115 of the 128 B/clk the port delivers, on top of the TMA fills), and the fill traffic per CTA drops likewise.
-  // Barriers: `full` lives in the leader (its own arrive.expect_tx for both CTAs' bytes + the peer's remote arrive; both
-  // CTAs' TMA loads signal it), `empty` and `tfull` are signalled in both CTAs by multicast commits, `tempty` collects the
-  // epilogue warps of both CTAs in the leader.
+  // CL = 2: the two CTAs of a cluster work on M-adjacent tiles of the same N tile; each loads half of the W tile and
+  // multicasts it to both, so a W tile crosses the L2 -> SM path once per 256 rows instead of once per 128 (the big-K
+  // GEMMs run at the 64 B/clk/SM limit of that path).  A slot may be refilled once BOTH CTAs have consumed it: the MMA
+  // commits arrive on the `empty` barrier of both CTAs (count 2).
   const int crank = CL == 2 ? static_cast<int>(cluster_ctarank()) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], CL);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], CL * kEpiWarps);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     if (STAGED) {
       tma_prefetch_desc(&tmOut);
@@ -750,13 +742,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) {
-    if (CL == 2) {
-      tmem_alloc_pair(tmem_slot, kTmemCols);
-      tmem_relinquish_pair();
-    } else {
-      tmem_alloc(tmem_slot, kTmemCols);
-      tmem_relinquish();
-    }
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -789,19 +776,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * stage_bytes;
-          if (CL == 2) {
-            const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            if (crank == 0) mbar_arrive_expect_tx_warp(&full_bar[stage], 2u * static_cast<uint32_t>(stage_bytes));
-            else if (lane == 0) mbar_arrive_cluster(lead_full);
-            __syncwarp();
-            tma_load_5d_pair_warp(sa, &tmA, lead_full, kc * kBlockK, c1, c2, c3, c4);
-            tma_load_2d_pair_warp(sa + kABytes, &tmB, lead_full, (tap * p.kchunks + kc) * kBlockK,
-                                  n_tile * p.bn + crank * half_rows);
-          } else {
-            mbar_arrive_expect_tx_warp(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            tma_load_5d_warp(sa, &tmA, &full_bar[stage], kc * kBlockK, c1, c2, c3, c4);
+          mbar_arrive_expect_tx_warp(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+          tma_load_5d_warp(sa, &tmA, &full_bar[stage], kc * kBlockK, c1, c2, c3, c4);
+          if (CL == 2)
+            tma_load_2d_multicast_warp(sa + kABytes + crank * half_rows * 128, &tmB, &full_bar[stage],
+                                       (tap * p.kchunks + kc) * kBlockK, n_tile * p.bn + crank * half_rows, 3);
+          else
             tma_load_2d_warp(sa + kABytes, &tmB, &full_bar[stage], (tap * p.kchunks + kc) * kBlockK, n_tile * p.bn);
-          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -809,8 +790,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 && (CL == 1 || crank == 0)) {
-    // ===================== MMA issuer (whole warp, one elected lane issues; CL = 2: the leader CTA only) =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -832,24 +813,22 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in 16-byte units
-          if (CL == 2) umma_f16_ss_pair_warp(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          else umma_f16_ss_warp(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_f16_ss_warp(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        if (CL == 2) umma_commit_pair_warp(&empty_bar[stage], 3);   // frees the slot in BOTH CTAs
+        if (CL == 2) umma_commit_multicast_warp(&empty_bar[stage], 3);   // the slot is free in BOTH CTAs' books
         else umma_commit_warp(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      if (CL == 2) umma_commit_pair_warp(&tfull_bar[as], 3);   // both CTAs' epilogues
-      else umma_commit_warp(&tfull_bar[as]);  // accumulator complete -> epilogue
+      umma_commit_warp(&tfull_bar[as]);  // accumulator complete -> epilogue
       if (tr && mt < 64) p.trace[16 * mt + 6] = clock64();
       ++mt;
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
-  } else if (warp >= 2) {
+  } else {
     // ===================== epilogue warps =====================
     if (STAGED)
       epilogue_staged<MODE, NRES, LNF, CL>(p, &tmOut, &tmRes, tmem_base, tfull_bar, tempty_bar, res_bar, sbias_all, tbuf, warp,
@@ -863,8 +842,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (CL == 2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
-    if (CL == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
-    else tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1024,9 +1002,9 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     return CCEDIT_ERR_CUDA;
   }
 
-  // CTA pairs (tcgen05 cta_group::2, 256 x BN tiles): for the GEMMs whose K loop is long enough that the tile is paced by
-  // operand delivery (convolutions, temporal k3, K >= 640 linears).  CCEDIT_GEMM_CLUSTER: 0 = never, 1 = default rule,
-  // 2 = wherever possible.
+  // Clusters of two CTAs sharing the W tiles (TMA multicast): for the GEMMs whose K loop is long enough that the tile is
+  // paced by operand delivery over the L2 -> SM path (convolutions, temporal k3, K >= 640 linears) and that have at least
+  // one pair of M tiles per SM pair.  CCEDIT_GEMM_CLUSTER: 0 = never, 1 = default rule, 2 = wherever possible.
   static const int cluster_mode = [] { const char* e = getenv("CCEDIT_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
   long long m_tiles_all = 1;
   for (int i = 0; i < 4; ++i) m_tiles_all *= (d->out_dims[i] + d->box[i] - 1) / d->box[i];
@@ -1099,9 +1077,9 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.flags = d->flags;
   static const int dev_flags = [] { const char* e = getenv("CCEDIT_GEMM_DEV"); return e ? atoi(e) << 8 : 0; }();
   p.flags |= dev_flags;                                                           // developer experiments only
-  p.idesc = umma_idesc_f16(cl * kBlockM, d->bn);          // cl = 2: one instruction spans the pair, M = 256
+  p.idesc = umma_idesc_f16(kBlockM, d->bn);
   p.trace = g_trace_buf;
-  const int stage_bytes = kABytes + (d->bn / cl) * kBlockK * 2;
+  const int stage_bytes = kABytes + d->bn * kBlockK * 2;
   const int kblocks = d->ntaps * p.kchunks;
   const int nres = (d->res1 ? 1 : 0) + (d->res2 ? 1 : 0);
   if (d->res2 && !d->res1) {
