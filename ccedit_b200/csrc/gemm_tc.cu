@@ -760,6 +760,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
+    // An mbarrier wait costs 100-200 clocks even when its phase completed long ago (TRYWAIT latency); with one wait per
+    // 64-wide k-block the producer (and the MMA issuer below) needed ~350 clocks per block - more than the 320 clocks
+    // the tensor core spends on a 128 x 160 x 64 block, which is why the BN = 160 GEMMs ran at 67-80 % pipe activity
+    // while BN = 256 (512 clocks per block) did not care.  The NEXT slot's barrier is therefore probed with a
+    // non-blocking test issued ahead of this block's TMA / MMA instructions; the blocking wait is only the fallback.
+    bool slot_free = false;
     const int half_rows = p.bn >> 1;         // CL = 2: W rows this CTA fetches (and multicasts) per stage
     for (int tile = it0; tile < ittotal; tile += itstep) {
       const int n_tile = tile % p.n_tiles;
@@ -774,8 +780,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int c1 = o[0] + p.taps[tap][0], c2 = o[1] + p.taps[tap][1];
         const int c3 = o[2] + p.taps[tap][2], c4 = o[3] + p.taps[tap][3];
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (!slot_free) mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * stage_bytes;
+          {
+            const int ns = stage + 1 == p.stages ? 0 : stage + 1;
+            slot_free = mbar_test_wait(&empty_bar[ns], (ns == 0 ? phase ^ 1u : phase) ^ 1u);
+          }
           mbar_arrive_expect_tx_warp(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
           tma_load_5d_warp(sa, &tmA, &full_bar[stage], kc * kBlockK, c1, c2, c3, c4);
           if (CL == 2)
@@ -797,6 +807,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     int mt = 0;
+    bool slot_full = false;                  // probe of the next slot's `full` barrier (see the producer)
     const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
     for (int tile = it0; tile < ittotal; tile += itstep) {
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
@@ -804,8 +815,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (tr && mt < 64) p.trace[16 * mt + 5] = clock64();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * kAccStride);
       for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        if (!slot_full) mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
+        {
+          const int ns = stage + 1 == p.stages ? 0 : stage + 1;
+          slot_full = mbar_test_wait(&full_bar[ns], ns == 0 ? phase ^ 1u : phase);
+        }
         if (kb == 0 && tr && mt < 64) p.trace[16 * mt + 7] = clock64();
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint64_t adesc = umma_desc_k_sw128(sa);
