@@ -62,7 +62,10 @@ def broadcast_weights(module: torch.nn.Module, src: int = 0, bucket_bytes: int =
                     off += b.numel()
                 total += size
                 bucket, size = [], 0
-    if hasattr(module, "invalidate_packed"):
+    # the copies above go through `.data` (no version bump): drop packed fp16 copies / captured graphs explicitly
+    if hasattr(module, "invalidate"):
+        module.invalidate()
+    elif hasattr(module, "invalidate_packed"):
         module.invalidate_packed()
     return total
 
