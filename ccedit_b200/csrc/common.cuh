@@ -259,6 +259,65 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {       // every thread of every CTA of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// ---- CTA pairs (tcgen05 cta_group::2): one MMA instruction of the leader CTA drives the tensor cores of both SMs ----
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {          // arrive on a (possibly remote) barrier
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are signalled on `bar_cluster`,
+// a shared::cluster address that may belong to the peer (the leader's `full` barrier)
+__device__ __forceinline__ void tma_load_2d_pair_warp(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair_warp(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                      int c2, int c3, int c4) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];\n\t}" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem of both CTAs: 128 rows each] * B[smem of both CTAs: N/2 rows each]^T, issued by the leader
+__device__ __forceinline__ void umma_f16_ss_pair_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_warp(uint64_t* bar, uint16_t mask) {   // arrives in every CTA of `mask`
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 // 2-D tile load delivered to the same shared-memory offset (and signalling the same mbarrier offset) in every CTA of `mask`
 __device__ __forceinline__ void tma_load_2d_multicast_warp(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                                            uint16_t mask) {

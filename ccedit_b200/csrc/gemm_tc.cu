@@ -201,12 +201,12 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
   int titer = 0;
   int staged_ntile = -1;                // N tile whose bias row (and column sums) sit in sbias / scs
-  const int it0 = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int itstep = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int ittotal = CL == 2 ? p.total_pairs : p.total_tiles;
+  const int it0 = CL >= 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int itstep = CL >= 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int ittotal = CL >= 2 ? p.total_pairs : p.total_tiles;
   for (int tile = it0; tile < ittotal; tile += itstep) {
     if (tracing && titer < 64) p.trace[16 * titer + 0] = clock64();
-    if (CL == 2) pair_digits(p, tile, crank, dig);
+    if (CL >= 2) pair_digits(p, tile, crank, dig);
     const int n_tile = dig[0];
     bool valid = true;
     long long off_o = lo_o, off_r1 = lo_r1, off_r2 = lo_r2;
@@ -372,7 +372,10 @@ __device__ __forceinline__ void epilogue_loop(const GemmKParams& p, uint32_t tme
     if (tracing && titer < 64) p.trace[16 * titer + 3] = clock64();
     tcgen05_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    if (lane == 0) {                    // CL = 3: the accumulators of BOTH CTAs are released on the leader's barrier
+      if (CL == 3) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      else mbar_arrive(&tempty_bar[as]);
+    }
     if (tracing && titer < 64) p.trace[16 * titer + 4] = clock64();
     ++titer;
     as ^= 1;
@@ -448,10 +451,10 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
       inc[i] = g % radix[i]; g /= radix[i];
     }
   }
-  const int it0 = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int itstep = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int ittotal = CL == 2 ? p.total_pairs : p.total_tiles;
-  if (CL == 2) pair_digits(p, it0, crank, dig);
+  const int it0 = CL >= 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int itstep = CL >= 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int ittotal = CL >= 2 ? p.total_pairs : p.total_tiles;
+  if (CL >= 2) pair_digits(p, it0, crank, dig);
   // residual of the first tile
   if (NRES >= 1 && it0 < ittotal && lane == 0) {
     mbar_arrive_expect_tx(&rbar[0], static_cast<uint32_t>(32 * W * 2));
@@ -503,7 +506,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
     const __half* r2ptr = p.res2 + off_r2 + col0_out;        // dereferenced only if NRES >= 2 and valid
     // next tile (mixed-radix add with carry)
     int ndig[5];
-    if (CL == 2) {
+    if (CL >= 2) {
       pair_digits(p, tile + itstep, crank, ndig);
     } else {
       int carry = 0;
@@ -670,7 +673,8 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
     fence_proxy_async_smem();                                // this thread's staging writes -> visible to the TMA store
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(&tempty_bar[as]);
+      if (CL == 3) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      else mbar_arrive(&tempty_bar[as]);
       for (int bk = 0; bk < nblk; ++bk)
         tma_store_5d(tmOut, region + bk * blk_bytes, n_tile * ncols_out + eg * W + bk * p.cb, dig[1] * p.box[0] + qoff[0],
                      dig[2] * p.box[1] + qoff[1], dig[3] * p.box[2] + qoff[2], dig[4] * p.box[3] + qoff[3]);
@@ -704,7 +708,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);  // SWIZZLE_128B wants 1024 B alignment
 
-  const int stage_bytes = kABytes + p.bn * kBlockK * 2;
+  const int stage_bytes = kABytes + (CL == 3 ? p.bn / 2 : p.bn) * kBlockK * 2;   // CL = 3: this CTA holds half of the W tile
   // [stages x (A, B)] [STAGED: nbuf tile buffers] [barriers, 512 B] [per-warp bias rows]; every part a multiple of 1 KiB
   uint8_t* tbuf = smem + p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tbuf + (STAGED ? p.nbuf * p.tbuf_bytes : 0));
@@ -721,18 +725,23 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // multicasts it to both, so a W tile crosses the L2 -> SM path once per 256 rows instead of once per 128 (the big-K
   // GEMMs run at the 64 B/clk/SM limit of that path).  A slot may be refilled once BOTH CTAs have consumed it: the MMA
   // commits arrive on the `empty` barrier of both CTAs (count 2).
-  const int crank = CL == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  // CL = 3 (experimental, CCEDIT_GEMM_CLUSTER=3): a CTA PAIR on tcgen05 cta_group::2 computes a 256 x BN tile; each CTA
+  // loads its own A tile and half of the W tile (no multicast: the pair's MMA reads W from both shared memories), the
+  // leader (rank 0) issues one M = 256 instruction per k-step.  `full` lives in the leader: its arrive.expect_tx covers
+  // both CTAs' bytes and both CTAs' TMA loads (cp.async.bulk.tensor.cta_group::2) signal it; `empty` / `tfull` are
+  // signalled in both CTAs by multicast commits; `tempty` collects the epilogue warps of both CTAs in the leader.
+  const int crank = CL >= 2 ? static_cast<int>(cluster_ctarank()) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);
+      mbar_init(&empty_bar[s], CL == 2 ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tempty_bar[s], CL == 3 ? 2 * kEpiWarps : kEpiWarps);
     }
     if (STAGED) {
       tma_prefetch_desc(&tmOut);
@@ -742,19 +751,24 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CL == 3) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();          // the peer's barriers are initialised before anything can arrive on them
+  if (CL >= 2) cluster_sync_all();          // the peer's barriers are initialised before anything can arrive on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int kblocks = p.ntaps * p.kchunks;
-  const int it0 = CL == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int itstep = CL == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int ittotal = CL == 2 ? p.total_pairs : p.total_tiles;
+  const int it0 = CL >= 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int itstep = CL >= 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int ittotal = CL >= 2 ? p.total_pairs : p.total_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp, one elected lane issues) =====================
@@ -769,7 +783,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half_rows = p.bn >> 1;         // CL = 2: W rows this CTA fetches (and multicasts) per stage
     for (int tile = it0; tile < ittotal; tile += itstep) {
       const int n_tile = tile % p.n_tiles;
-      int m = CL == 2 ? 2 * (tile / p.n_tiles) + crank : tile / p.n_tiles;
+      int m = CL >= 2 ? 2 * (tile / p.n_tiles) + crank : tile / p.n_tiles;
       int o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -786,6 +800,19 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int ns = stage + 1 == p.stages ? 0 : stage + 1;
             slot_free = mbar_test_wait(&empty_bar[ns], (ns == 0 ? phase ^ 1u : phase) ^ 1u);
           }
+          if (CL == 3) {
+            // the leader's arrive.expect_tx accounts for both CTAs' bytes (count 1: the peer does not arrive at all)
+            const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_arrive_expect_tx_warp(&full_bar[stage], 2u * static_cast<uint32_t>(stage_bytes));
+            tma_load_5d_pair_warp(sa, &tmA, lead_full, kc * kBlockK, c1, c2, c3, c4);
+            tma_load_2d_pair_warp(sa + kABytes, &tmB, lead_full, (tap * p.kchunks + kc) * kBlockK,
+                                  n_tile * p.bn + crank * half_rows);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx_warp(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
           tma_load_5d_warp(sa, &tmA, &full_bar[stage], kc * kBlockK, c1, c2, c3, c4);
           if (CL == 2)
@@ -800,8 +827,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+  } else if (warp == 1 && (CL != 3 || crank == 0)) {
+    // ===================== MMA issuer (whole warp, one elected lane issues; CL = 3: the leader CTA only) =====================
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -828,22 +855,25 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // advance 16 elements (32 B) inside the 128 B swizzle row: +2 in 16-byte units
-          umma_f16_ss_warp(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          if (CL == 3) umma_f16_ss_pair_warp(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          else umma_f16_ss_warp(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        if (CL == 2) umma_commit_multicast_warp(&empty_bar[stage], 3);   // the slot is free in BOTH CTAs' books
+        if (CL == 3) umma_commit_pair_warp(&empty_bar[stage], 3);        // frees the slot in both CTAs of the pair
+        else if (CL == 2) umma_commit_multicast_warp(&empty_bar[stage], 3);   // the slot is free in BOTH CTAs' books
         else umma_commit_warp(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit_warp(&tfull_bar[as]);  // accumulator complete -> epilogue
+      if (CL == 3) umma_commit_pair_warp(&tfull_bar[as], 3);   // both CTAs' epilogues
+      else umma_commit_warp(&tfull_bar[as]);  // accumulator complete -> epilogue
       if (tr && mt < 64) p.trace[16 * mt + 6] = clock64();
       ++mt;
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue warps =====================
     if (STAGED)
       epilogue_staged<MODE, NRES, LNF, CL>(p, &tmOut, &tmRes, tmem_base, tfull_bar, tempty_bar, res_bar, sbias_all, tbuf, warp,
@@ -854,10 +884,11 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   tcgen05_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+  if (CL >= 2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CL == 3) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -915,7 +946,7 @@ static cudaError_t launch_gemm_t(const CUtensorMap* tm, const GemmKParams& p, in
     const int sms = device_sm_count();
     if (sms <= 0) return cudaErrorInvalidDevice;
     capacity = sms;
-    if (CL == 2) {
+    if (CL >= 2) {
       cudaLaunchConfig_t q;
       memset(&q, 0, sizeof(q));
       q.gridDim = dim3(2 * (sms / 2));
@@ -961,6 +992,9 @@ static cudaError_t launch_gemm_t(const CUtensorMap* tm, const GemmKParams& p, in
 template <int MODE, int NRES, bool LNF = false>
 static cudaError_t launch_gemm(const CUtensorMap* tm, const GemmKParams& p, bool staged, int cl, int smem_bytes,
                                cudaStream_t stream) {
+  if (cl == 3)
+    return staged ? launch_gemm_t<MODE, NRES, true, LNF, 3>(tm, p, p.total_pairs, smem_bytes, stream)
+                  : launch_gemm_t<MODE, NRES, false, LNF, 3>(tm, p, p.total_pairs, smem_bytes, stream);
   if (cl == 2)
     return staged ? launch_gemm_t<MODE, NRES, true, LNF, 2>(tm, p, p.total_pairs, smem_bytes, stream)
                   : launch_gemm_t<MODE, NRES, false, LNF, 2>(tm, p, p.total_pairs, smem_bytes, stream);
@@ -1017,14 +1051,17 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     return CCEDIT_ERR_CUDA;
   }
 
-  // Clusters of two CTAs sharing the W tiles (TMA multicast): for the GEMMs whose K loop is long enough that the tile is
-  // paced by operand delivery over the L2 -> SM path (convolutions, temporal k3, K >= 640 linears) and that have at least
-  // one pair of M tiles per SM pair.  CCEDIT_GEMM_CLUSTER: 0 = never, 1 = default rule, 2 = wherever possible.
-  static const int cluster_mode = [] { const char* e = getenv("CCEDIT_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
+  // Clusters of two CTAs on M-adjacent tiles of one N tile, for the GEMMs whose K loop is long enough that the tile is
+  // paced by operand delivery (convolutions, temporal k3, K >= 640 linears: k-loops of >= 10 blocks).
+  // CCEDIT_GEMM_CLUSTER: 0 = never; 1 = TMA multicast of the W tile (CL = 2) under that rule, 2 = wherever possible;
+  // 3 = CTA-pair MMA (CL = 3, tcgen05 cta_group::2, M = 256; default) under that rule, 4 = wherever possible.
+  static const int cluster_mode = [] { const char* e = getenv("CCEDIT_GEMM_CLUSTER"); return e ? atoi(e) : 3; }();
   long long m_tiles_all = 1;
   for (int i = 0; i < 4; ++i) m_tiles_all *= (d->out_dims[i] + d->box[i] - 1) / d->box[i];
   const int kblocks_all = d->ntaps * (d->kpad / kBlockK);
-  const int cl = (cluster_mode == 2 || (cluster_mode == 1 && kblocks_all >= 10)) && m_tiles_all >= 2 ? 2 : 1;
+  const bool cl_rule = cluster_mode == 2 || cluster_mode == 4 || ((cluster_mode == 1 || cluster_mode == 3) && kblocks_all >= 10);
+  const int cl = (cl_rule && m_tiles_all >= 2) ? (cluster_mode >= 3 ? 3 : 2) : 1;
+  const int wsplit = cl >= 2 ? 2 : 1;                    // W rows per TMA box = bn / wsplit
 
   CUtensorMap tm[4];
   CUtensorMap& tmA = tm[0];
@@ -1049,7 +1086,7 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->ntaps * d->kpad, (cuuint64_t)d->n};
     cuuint64_t strides[1] = {(cuuint64_t)d->ntaps * d->kpad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(d->bn / cl)};   // cl = 2: each CTA fetches half of the W tile
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(d->bn / wsplit)};   // clusters: each CTA fetches half of the W tile
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1092,9 +1129,9 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
   p.flags = d->flags;
   static const int dev_flags = [] { const char* e = getenv("CCEDIT_GEMM_DEV"); return e ? atoi(e) << 8 : 0; }();
   p.flags |= dev_flags;                                                           // developer experiments only
-  p.idesc = umma_idesc_f16(kBlockM, d->bn);
+  p.idesc = umma_idesc_f16(cl == 3 ? 2 * kBlockM : kBlockM, d->bn);   // pair MMA: one instruction spans both CTAs, M = 256
   p.trace = g_trace_buf;
-  const int stage_bytes = kABytes + d->bn * kBlockK * 2;
+  const int stage_bytes = kABytes + (cl == 3 ? d->bn / 2 : d->bn) * kBlockK * 2;
   const int kblocks = d->ntaps * p.kchunks;
   const int nres = (d->res1 ? 1 : 0) + (d->res2 ? 1 : 0);
   if (d->res2 && !d->res1) {
