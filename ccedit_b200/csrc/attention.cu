@@ -231,14 +231,16 @@ template <int DP>
 static int launch_fa(const FaParams& p, int frames, int heads, cudaStream_t st) {
   constexpr int DS = DP + 8;
   const int smem = (kFaBM + 4 * kFaBN) * DS * 2;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<bool> attr_done[kMaxDevices];        // function attributes belong to a device
+  const int dev = current_device();
+  CCEDIT_CHECK_ARG(dev >= 0, "ccedit_attention: no current CUDA device");
+  if (!attr_done[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_last_error("ccedit_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return CCEDIT_ERR_CUDA;
     }
-    attr_done = true;
+    attr_done[dev].store(true, std::memory_order_release);
   }
   dim3 grid((p.lq + kFaBM - 1) / kFaBM, heads, frames);
   flash_attn_kernel<DP><<<grid, kFaThreads, smem, st>>>(p);
@@ -408,14 +410,16 @@ static int launch_ta(const __half* q, long long ldq, const __half* k, long long 
   while (hpb > 1 && (smem_for(hpb) > 72 * 1024 || heads % hpb != 0)) --hpb;   // <= 72 KB: three CTAs per SM
   const size_t smem = smem_for(hpb);
   CCEDIT_CHECK_ARG(smem <= 227 * 1024, "ccedit_temporal_attention: T*d too large for shared memory (%zu bytes)", smem);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<bool> attr_done[kMaxDevices];
+  const int dev = current_device();
+  CCEDIT_CHECK_ARG(dev >= 0, "ccedit_temporal_attention: no current CUDA device");
+  if (!attr_done[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel<DP, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_last_error("ccedit_temporal_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return CCEDIT_ERR_CUDA;
     }
-    attr_done = true;
+    attr_done[dev].store(true, std::memory_order_release);
   }
   const int warps = hpb < 8 ? hpb : 8;
   const dim3 grid(static_cast<unsigned>(static_cast<long long>(B) * HW), heads / hpb);

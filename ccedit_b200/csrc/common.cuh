@@ -157,6 +157,38 @@ __device__ __forceinline__ void bulk_wait_group_read() {   // at most N groups s
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// Warp-collective forms of the TMA store / bulk-group / mbarrier operations of the staged GEMM epilogue: the whole
+// converged warp calls them with warp-uniform operands and the elected lane issues (the same lane every time: bulk
+// async-groups belong to the issuing thread).  From inside `if (lane == 0)` each of these costs an ELECT / R2UR loop.
+__device__ __forceinline__ void tma_store_5d_warp(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3,
+                                                  int c4) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];\n\t}"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group_warp() {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e cp.async.bulk.commit_group;\n\t}" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read_warp() {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e cp.async.bulk.wait_group.read %0;\n\t}" ::"n"(N)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_warp(uint32_t cluster_addr) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n\t}"
+      ::"r"(cluster_addr)
+      : "memory");
+}
+
 // warp-collective TMA issue (see umma_*_warp below): whole converged warp calls, one elected lane issues
 __device__ __forceinline__ void mbar_arrive_expect_tx_warp(uint64_t* bar, uint32_t bytes) {
   asm volatile(

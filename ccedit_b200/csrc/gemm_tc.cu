@@ -456,12 +456,13 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
   const int ittotal = CL >= 2 ? p.total_pairs : p.total_tiles;
   if (CL >= 2) pair_digits(p, it0, crank, dig);
   // residual of the first tile
-  if (NRES >= 1 && it0 < ittotal && lane == 0) {
-    mbar_arrive_expect_tx(&rbar[0], static_cast<uint32_t>(32 * W * 2));
+  // (all TMA / bulk-group / barrier operations of this epilogue are warp-collective: converged warp, elected lane)
+  if (NRES >= 1 && it0 < ittotal) {
+    mbar_arrive_expect_tx_warp(&rbar[0], static_cast<uint32_t>(32 * W * 2));
     for (int bk = 0; bk < nblk; ++bk)
-      tma_load_5d(region0 + bk * blk_bytes, tmRes, &rbar[0], dig[0] * ncols_out + eg * W + bk * p.cb,
-                  dig[1] * p.box[0] + qoff[0], dig[2] * p.box[1] + qoff[1], dig[3] * p.box[2] + qoff[2],
-                  dig[4] * p.box[3] + qoff[3]);
+      tma_load_5d_warp(region0 + bk * blk_bytes, tmRes, &rbar[0], dig[0] * ncols_out + eg * W + bk * p.cb,
+                       dig[1] * p.box[0] + qoff[0], dig[2] * p.box[1] + qoff[1], dig[3] * p.box[2] + qoff[2],
+                       dig[4] * p.box[3] + qoff[3]);
   }
   __syncwarp();
 
@@ -563,21 +564,19 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
     if (tracing && it < 64) p.trace[16 * it + 2] = clock64();
     uint8_t* region = region0 + b * p.tbuf_bytes;
     if (NRES >= 1) {
-      if (p.nbuf == 2 && has_next && lane == 0) {
-        bulk_wait_group_read<0>();                         // the store of tile it-1 has left the other buffer
+      if (p.nbuf == 2 && has_next) {
+        bulk_wait_group_read_warp<0>();                    // the store of tile it-1 has left the other buffer
         uint8_t* other = region0 + (b ^ 1) * p.tbuf_bytes;
-        mbar_arrive_expect_tx(&rbar[b ^ 1], static_cast<uint32_t>(32 * W * 2));
+        mbar_arrive_expect_tx_warp(&rbar[b ^ 1], static_cast<uint32_t>(32 * W * 2));
         for (int bk = 0; bk < nblk; ++bk)
-          tma_load_5d(other + bk * blk_bytes, tmRes, &rbar[b ^ 1], ndig[0] * ncols_out + eg * W + bk * p.cb,
-                      ndig[1] * p.box[0] + qoff[0], ndig[2] * p.box[1] + qoff[1], ndig[3] * p.box[2] + qoff[2],
-                      ndig[4] * p.box[3] + qoff[3]);
+          tma_load_5d_warp(other + bk * blk_bytes, tmRes, &rbar[b ^ 1], ndig[0] * ncols_out + eg * W + bk * p.cb,
+                           ndig[1] * p.box[0] + qoff[0], ndig[2] * p.box[1] + qoff[1], ndig[3] * p.box[2] + qoff[2],
+                           ndig[4] * p.box[3] + qoff[3]);
       }
       mbar_wait(&rbar[b], b ? rph1 : rph0);
       if (b) rph1 ^= 1u; else rph0 ^= 1u;
     } else {
-      if (lane == 0) {
-        if (p.nbuf == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();   // this buffer's last store has been read
-      }
+      if (p.nbuf == 2) bulk_wait_group_read_warp<1>(); else bulk_wait_group_read_warp<0>();   // this buffer's last store has been read
     }
     __syncwarp();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(as * kAccStride) +
@@ -672,21 +671,19 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
     tcgen05_fence_before();
     fence_proxy_async_smem();                                // this thread's staging writes -> visible to the TMA store
     __syncwarp();
-    if (lane == 0) {
-      if (CL == 3) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
-      else mbar_arrive(&tempty_bar[as]);
+    if (CL == 3) mbar_arrive_cluster_warp(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+    else mbar_arrive_warp(&tempty_bar[as]);
+    for (int bk = 0; bk < nblk; ++bk)
+      tma_store_5d_warp(tmOut, region + bk * blk_bytes, n_tile * ncols_out + eg * W + bk * p.cb, dig[1] * p.box[0] + qoff[0],
+                        dig[2] * p.box[1] + qoff[1], dig[3] * p.box[2] + qoff[2], dig[4] * p.box[3] + qoff[3]);
+    bulk_commit_group_warp();
+    if (NRES >= 1 && p.nbuf == 1 && has_next) {
+      bulk_wait_group_read_warp<0>();
+      mbar_arrive_expect_tx_warp(&rbar[0], static_cast<uint32_t>(32 * W * 2));
       for (int bk = 0; bk < nblk; ++bk)
-        tma_store_5d(tmOut, region + bk * blk_bytes, n_tile * ncols_out + eg * W + bk * p.cb, dig[1] * p.box[0] + qoff[0],
-                     dig[2] * p.box[1] + qoff[1], dig[3] * p.box[2] + qoff[2], dig[4] * p.box[3] + qoff[3]);
-      bulk_commit_group();
-      if (NRES >= 1 && p.nbuf == 1 && has_next) {
-        bulk_wait_group_read<0>();
-        mbar_arrive_expect_tx(&rbar[0], static_cast<uint32_t>(32 * W * 2));
-        for (int bk = 0; bk < nblk; ++bk)
-          tma_load_5d(region0 + bk * blk_bytes, tmRes, &rbar[0], ndig[0] * ncols_out + eg * W + bk * p.cb,
-                      ndig[1] * p.box[0] + qoff[0], ndig[2] * p.box[1] + qoff[1], ndig[3] * p.box[2] + qoff[2],
-                      ndig[4] * p.box[3] + qoff[3]);
-      }
+        tma_load_5d_warp(region0 + bk * blk_bytes, tmRes, &rbar[0], ndig[0] * ncols_out + eg * W + bk * p.cb,
+                         ndig[1] * p.box[0] + qoff[0], ndig[2] * p.box[1] + qoff[1], ndig[3] * p.box[2] + qoff[2],
+                         ndig[4] * p.box[3] + qoff[3]);
     }
     __syncwarp();
     if (tracing && it < 64) p.trace[16 * it + 4] = clock64();
@@ -695,7 +692,7 @@ __device__ __forceinline__ void epilogue_staged(const GemmKParams& p, const CUte
 #pragma unroll
     for (int i = 0; i < 5; ++i) dig[i] = ndig[i];
   }
-  if (lane == 0) bulk_wait_group_read<0>();                  // shared memory must outlive the last store's read
+  bulk_wait_group_read_warp<0>();                            // shared memory must outlive the last store's read
   __syncwarp();
 }
 
@@ -1192,7 +1189,9 @@ static int gemm_impl(const ccedit_gemm_desc* d, cudaStream_t stream) {
     tm[2] = tm[0];
     tm[3] = tm[0];
   }
-  int stages = (staged ? budget - p.nbuf * p.tbuf_bytes : (192 * 1024 < budget ? 192 * 1024 : budget)) / stage_bytes;
+  // direct epilogue: 192 KB of stages (5 x 36 KB at BN = 160); the CTA-pair kernel's smaller stages (26 KB) take the whole
+  // budget: 8 stages = 2 560 tensor-clocks of operands in flight
+  int stages = (staged ? budget - p.nbuf * p.tbuf_bytes : ((cl != 3 && 192 * 1024 < budget) ? 192 * 1024 : budget)) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   const int smem_bytes = stages * stage_bytes + (staged ? p.nbuf * p.tbuf_bytes : 0) + fixed_bytes;
