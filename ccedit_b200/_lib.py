@@ -96,6 +96,9 @@ SIGNATURES = {
     "ccedit_hint_stem01": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "ccedit_softmax_rows": (C.c_int, [_vp, _i64, _i64, _i32, _vp]),
     "ccedit_cl_to_ncthw": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i64, _vp]),
+    "ccedit_embed_tokens": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ccedit_quick_gelu": (C.c_int, [_vp, _i64, _vp]),
+    "ccedit_causal_attention_small": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp]),
     "ccedit_sampler_prepare": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "ccedit_sampler_mid": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp]),
     "ccedit_sampler_final": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i64, _vp]),

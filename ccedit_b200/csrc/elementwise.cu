@@ -469,3 +469,146 @@ extern "C" int ccedit_cl_to_ncthw(const void* src, int32_t ld, void* dst, int32_
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_cl_to_ncthw");
   return CCEDIT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Text conditioner (CLIP-L text transformer): the three operations the tap-GEMM / LayerNorm kernels do
+// not cover.  All tiny (77 tokens per prompt, once per clip): written for clarity, not for a roofline.
+// ---------------------------------------------------------------------------------------------------------------
+namespace ccedit {
+
+// out[b*L + l][:] = token_emb[ids[b][l]][:] + pos_emb[l][:]   (fp16 tables, fp32 add, fp16 out); D % 8 == 0
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const __half* __restrict__ tok,
+                                    const __half* __restrict__ pos, __half* __restrict__ out, int L, int D, int V, long long rows) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // over rows * D/8
+  const int nvec = D >> 3;
+  if (i >= rows * nvec) return;
+  const long long r = i / nvec;
+  const int cv = static_cast<int>(i % nvec);
+  long long id = ids[r];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(tok + id * D) + cv);
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(pos + (r % L) * D) + cv);
+  reinterpret_cast<uint4*>(out + r * D)[cv] = add8(a, b);
+}
+
+// x = x * sigmoid(1.702 x) in place (CLIP's quick_gelu), fp16 storage, fp32 math
+__global__ void quick_gelu_kernel(__half* __restrict__ x, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  uint4 u = reinterpret_cast<uint4*>(x)[i];
+  uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    f.x = __fdividef(f.x, 1.0f + __expf(-1.702f * f.x));
+    f.y = __fdividef(f.y, 1.0f + __expf(-1.702f * f.y));
+    const __half2 h = __floats2half2_rn(f.x, f.y);
+    w[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  reinterpret_cast<uint4*>(x)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Causal self-attention over a short sequence (L <= 128 tokens, head dim 64): one CTA per (batch entry, head), K and V of
+// the head staged in shared memory, one warp per query row (round-robin): lane j scores keys j, j+32, j+64, j+96 (j <= i),
+// warp-shuffle softmax, every lane accumulates two output channels.
+__global__ void __launch_bounds__(128) causal_attn_small_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                                const __half* __restrict__ v, __half* __restrict__ o,
+                                                                long long ld, long long ldo, int L, int heads, float scale) {
+  constexpr int D = 64;
+  extern __shared__ __half ca_sm[];                 // K [L][D+2], V [L][D+2] (padded rows: conflict-free column reads), P [4][128]
+  __half* sK = ca_sm;
+  __half* sV = ca_sm + L * (D + 2);
+  float* sP = reinterpret_cast<float*>(ca_sm + 2 * L * (D + 2));
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long base = static_cast<long long>(b) * L;
+  for (int idx = threadIdx.x; idx < L * (D / 2); idx += blockDim.x) {
+    const int r = idx / (D / 2), c2 = idx % (D / 2);
+    reinterpret_cast<__half2*>(sK + r * (D + 2))[c2] = reinterpret_cast<const __half2*>(k + (base + r) * ld + h * D)[c2];
+    reinterpret_cast<__half2*>(sV + r * (D + 2))[c2] = reinterpret_cast<const __half2*>(v + (base + r) * ld + h * D)[c2];
+  }
+  __syncthreads();
+  float* myP = sP + warp * 128;
+  for (int i = warp; i < L; i += 4) {
+    const __half2* qr = reinterpret_cast<const __half2*>(q + (base + i) * ld + h * D);
+    float2 qv[D / 2];
+#pragma unroll
+    for (int c = 0; c < D / 2; ++c) qv[c] = __half22float2(__ldg(qr + c));
+    float s[4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane + 32 * t;
+      s[t] = -INFINITY;
+      if (j <= i && j < L) {
+        const __half2* kr = reinterpret_cast<const __half2*>(sK + j * (D + 2));
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < D / 2; ++c) {
+          const float2 kv = __half22float2(kr[c]);
+          acc = fmaf(qv[c].x, kv.x, acc);
+          acc = fmaf(qv[c].y, kv.y, acc);
+        }
+        s[t] = acc * scale;
+      }
+      m = fmaxf(m, s[t]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float p = s[t] == -INFINITY ? 0.f : __expf(s[t] - m);
+      myP[lane + 32 * t] = p;
+      sum += p;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j <= i; ++j) {
+      const float p = myP[j];
+      const float2 vv = __half22float2(reinterpret_cast<const __half2*>(sV + j * (D + 2))[lane]);
+      o0 = fmaf(p, vv.x, o0);
+      o1 = fmaf(p, vv.y, o1);
+    }
+    const float inv = 1.f / sum;
+    reinterpret_cast<__half2*>(o + (base + i) * ldo + h * D)[lane] = __floats2half2_rn(o0 * inv, o1 * inv);
+    __syncwarp();
+  }
+}
+
+}  // namespace ccedit
+
+extern "C" int ccedit_embed_tokens(const int64_t* ids, const void* tok, const void* pos, void* out, int32_t B, int32_t L,
+                                   int32_t D, int32_t V, void* stream) {
+  CCEDIT_CHECK_ARG(ids && tok && pos && out && B > 0 && L > 0 && D > 0 && D % 8 == 0 && V > 0, "ccedit_embed_tokens: bad arguments");
+  const long long rows = static_cast<long long>(B) * L, total = rows * (D / 8);
+  embed_tokens_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), static_cast<const __half*>(tok), static_cast<const __half*>(pos),
+      static_cast<__half*>(out), L, D, V, rows);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_embed_tokens");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_quick_gelu(void* x, int64_t n, void* stream) {
+  CCEDIT_CHECK_ARG(x && n > 0 && n % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "ccedit_quick_gelu: bad arguments");
+  quick_gelu_kernel<<<blocks_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__half*>(x), n / 8);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_quick_gelu");
+  return CCEDIT_OK;
+}
+
+extern "C" int ccedit_causal_attention_small(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo,
+                                             int32_t B, int32_t L, int32_t heads, int32_t d, float scale, void* stream) {
+  CCEDIT_CHECK_ARG(q && k && v && o && B > 0 && L > 0 && L <= 128 && heads > 0 && d == 64 && ld % 2 == 0 && ldo % 2 == 0,
+                   "ccedit_causal_attention_small: bad arguments (L <= 128, d == 64)");
+  const size_t smem = static_cast<size_t>(2) * L * (64 + 2) * sizeof(__half) + 4 * 128 * sizeof(float);
+  causal_attn_small_kernel<<<B * heads, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v), static_cast<__half*>(o), ld,
+      ldo, L, heads, scale);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_causal_attention_small");
+  return CCEDIT_OK;
+}

@@ -690,3 +690,45 @@ def conv_s2_taps_asym():
             pw, ow = split(kw)
             taps.append((ow, oh, ph * 2 + pw, 0))
     return taps
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# text conditioner helpers (CLIP text transformer)
+# ---------------------------------------------------------------------------------------------------------------------
+def embed_tokens(ids: torch.Tensor, token_emb: torch.Tensor, pos_emb: torch.Tensor) -> torch.Tensor:
+    """ids int64 [B, L]; token_emb fp16 [V, D]; pos_emb fp16 [>= L, D] -> fp16 [B * L, D]."""
+    _require(token_emb, name="token_emb")
+    _require(pos_emb, name="pos_emb")
+    if not ids.is_cuda or ids.dtype != torch.int64:
+        raise RuntimeError("ccedit_b200.embed_tokens: ids must be a CUDA int64 tensor")
+    B, L = ids.shape
+    V, D = token_emb.shape
+    out = torch.empty(B * L, D, dtype=torch.float16, device=ids.device)
+    _call("embed_tokens", _lib.load().ccedit_embed_tokens,
+          (ids.contiguous().data_ptr(), token_emb.data_ptr(), pos_emb.data_ptr(), out.data_ptr(), B, L, D, V, _stream()),
+          nbytes=2 * _nb(out))
+    return out
+
+
+def quick_gelu_(x: torch.Tensor) -> torch.Tensor:
+    """x * sigmoid(1.702 x) in place on a contiguous fp16 tensor."""
+    _require(x, name="x")
+    if not x.is_contiguous():
+        raise RuntimeError("ccedit_b200.quick_gelu_: x must be contiguous")
+    _call("quick_gelu", _lib.load().ccedit_quick_gelu, (x.data_ptr(), x.numel(), _stream()), nbytes=2 * _nb(x))
+    return x
+
+
+def causal_attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, out: torch.Tensor,
+                           scale: Optional[float] = None) -> torch.Tensor:
+    """q, k, v: [B, L, heads*64] views sharing one row stride; causal softmax(q k^T * scale) v -> out [B, L, heads*64]."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _require(t, name=nm)
+    B, L, Cc = q.shape
+    dh = Cc // heads
+    if not (q.stride(1) == k.stride(1) == v.stride(1)) or q.stride(0) != L * q.stride(1):
+        raise RuntimeError("ccedit_b200.causal_attention_small: q, k, v must share a uniform row stride")
+    _call("causal_attention_small", _lib.load().ccedit_causal_attention_small,
+          (q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(1), out.data_ptr(), out.stride(1), B, L, heads, dh,
+           float(dh) ** -0.5 if scale is None else scale, _stream()), flops=4.0 * B * L * L * Cc, nbytes=4.0 * B * L * Cc * 2)
+    return out

@@ -207,6 +207,21 @@ int ccedit_cl_to_ncthw(const void* src, int32_t ld, void* dst, int32_t dst_f32, 
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Text conditioner: FrozenCLIPEmbedder (sgm/modules/encoders/modules.py:358-420) wraps HuggingFace
+ * transformers' CLIPTextModel (pinned 4.19.1 in the reference's requirements.txt:34; not vendored).  Its linears and
+ * LayerNorms run on ccedit_gemm (LayerNorm folded) / ccedit_layernorm; these three entry points cover the rest.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* out fp16 [B*L][D] = token_emb[ids[b][l]] + pos_emb[l]  (CLIPTextEmbeddings; ids int64 [B][L], tables fp16 [V][D], [L][D]). */
+int ccedit_embed_tokens(const int64_t* ids, const void* token_emb, const void* pos_emb, void* out, int32_t B, int32_t L,
+                        int32_t D, int32_t V, void* stream);
+/* x = x * sigmoid(1.702 x) in place, fp16 [n], n % 8 == 0  (CLIP's hidden_act "quick_gelu"). */
+int ccedit_quick_gelu(void* x, int64_t n, void* stream);
+/* Causal self-attention of a short sequence (CLIPAttention with the causal mask of CLIPTextTransformer): q, k, v fp16
+ * [B][L][*] with row stride ld (heads * 64 channels each), o [B][L][heads*64] row stride ldo; L <= 128, d == 64. */
+int ccedit_causal_attention_small(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, int32_t B,
+                                  int32_t L, int32_t heads, int32_t d, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Sampler step, fused: the elementwise math of DPMPP2SAncestralSampler.sampler_step
  * (sampling.py:385-407) + DiscreteDenoiser / EpsScaling (denoiser.py:22-40, denoiser_scaling.py:16-22) + VanillaCFG
  * (guiders.py:25-29, 56-67) around the two network calls of a step.  x, x2, x_euler, noise, x_out: fp32 [n] latents

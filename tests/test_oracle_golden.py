@@ -170,3 +170,19 @@ def test_vae_decode_and_encode_match_reference(vae_sd):
             assert rel_err(vo.decode_first_stage(vae_sd, gold[name]["inputs"][0]), gold[name]["output"]) < TOL
         g = gold["encode_moments"]
         assert rel_err(vo.encode_first_stage_moments(vae_sd, g["inputs"][0]), g["output"]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# text conditioner: the restatement of transformers' CLIPTextModel against the installed implementation
+# ---------------------------------------------------------------------------------------------------------------------
+def test_clip_text_oracle_matches_transformers():
+    pytest.importorskip("transformers")
+    from oracle import clip_oracle as co
+    from ccedit_b200.clip_text import CLIPTextModel
+    shapes = {k: tuple(v.shape) for k, v in CLIPTextModel().state_dict().items()}
+    sd = co.seeded_state_dict(shapes, seed=0)
+    ids = torch.randint(0, 49408, (2, 77), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        mine = co.clip_text_forward(sd, ids)
+    ref = co.transformers_reference(sd, ids)
+    assert rel_err(mine, ref) < TOL

@@ -75,3 +75,32 @@ def test_decode_headline_size_properties(vae):
     assert torch.equal(vae.decode(z, scale=1.0 / 0.18215), out)
     one = vae.decode(z[:, :, 5:6], scale=1.0 / 0.18215)
     assert rel_err(one, out[:, :, 5:6]) < VAE_TOL      # GroupNorm slicing (summation order) depends on the frame count
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# text conditioner (first half): CLIP-L text transformer against the oracle restatement of
+# transformers.CLIPTextModel on seeded weights and random token ids (no pretrained weights / vocabulary in this image)
+# ---------------------------------------------------------------------------------------------------------------------
+CLIP_TOL = 4.0e-3
+
+
+def test_clip_text_encoder_matches_oracle():
+    from oracle import clip_oracle as co
+    from ccedit_b200.clip_text import FrozenCLIPEmbedder
+    emb = FrozenCLIPEmbedder(device="cuda")
+    shapes = {k: tuple(v.shape) for k, v in emb.transformer.state_dict().items()}
+    sd = co.seeded_state_dict(shapes, seed=0)
+    emb.transformer.load_state_dict(sd, strict=True)
+    emb = emb.cuda()
+    ids = torch.randint(0, 49408, (2, 77), generator=torch.Generator().manual_seed(5))
+    out = emb(ids.cuda())
+    with torch.no_grad():
+        ref = co.clip_text_forward(sd, ids)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (2, 77, 768)
+    assert rel_err(out, ref) < CLIP_TOL
+    # causality: the first tokens do not depend on later ones
+    ids2 = ids.clone()
+    ids2[:, 40:] = 7
+    assert torch.equal(emb(ids2.cuda())[:, :40], out[:, :40])
+    with pytest.raises(RuntimeError, match="vocabulary"):
+        emb(["a bear walking"])
