@@ -102,5 +102,9 @@ def test_clip_text_encoder_matches_oracle():
     ids2 = ids.clone()
     ids2[:, 40:] = 7
     assert torch.equal(emb(ids2.cuda())[:, :40], out[:, :40])
-    with pytest.raises(RuntimeError, match="vocabulary"):
-        emb(["a bear walking"])
+    # strings go through transformers' CLIPTokenizer when its vocabulary is cached on the machine; otherwise a loud error
+    try:
+        z = emb(["a bear walking"])
+        assert tuple(z.shape) == (1, 77, 768) and torch.isfinite(z).all()
+    except RuntimeError as e:
+        assert "vocabulary" in str(e)
