@@ -643,7 +643,7 @@ def run_reference(args):
     t_call = sum(times) / len(times)
     fl = network_flops(kind, B, T, h, w)["total"]
     value = args.clips_per_gpu / (2 * t_call)
-    steps_run = len(times) / 2.0
+    steps_run = max(1, len(times) // 2)                  # whole sampler steps covered by the timed calls (2 calls per step)
     base = {"value": round(value, 6), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"oracle port (fp32, torch {torch.__version__}, {cores} threads): {len(times)} full-size network "
                       f"call(s) at CFG batch {B} x {T} keyframes x latent {h}x{w} = {fl / 1e12:.2f} TFLOP each, "
@@ -651,7 +651,7 @@ def run_reference(args):
             "seconds_per_call": [round(t, 2) for t in times]}
     res = {
         "impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps_run if steps_run != int(steps_run) else int(steps_run), "warmup": 0,
+        "steps": steps_run, "warmup": 0,
         "steps_requested": args.steps, "warmup_requested": args.warmup, "network_calls_timed": len(times),
         "ms_per_step": round(2e3 * t_call, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
