@@ -257,7 +257,11 @@ class FusedDPMPP2SAncestralSampler(DPMPP2SAncestralSampler):
                tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in sorted(cond.items())),
                tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in sorted(uc.items())))
         plan = self._plans.get(key)
+        wver = network._weights_version() if hasattr(network, "_weights_version") else None
         if plan is not None:
+            if plan["wver"] != wver:                     # weights changed (load_state_dict, LoRA merge, invalidate()):
+                plan["graphs"].clear()                   # the captured step graphs replay the old packed weights
+                plan["wver"] = wver
             return plan
         self._plans.clear()                                # one clip at a time: the static buffers are large
         dev, B, n = x.device, x.shape[0], x.numel()
@@ -271,7 +275,7 @@ class FusedDPMPP2SAncestralSampler(DPMPP2SAncestralSampler):
             net_call = lambda p: network.forward_cfg(p["xin2"][:B], p["t2"][:B], p["cc"])
         else:
             net_call = lambda p: network(p["xin2"], p["t2"], p["cc"])
-        plan = dict(net_call=net_call, dedup=dedup, sigmas=sigmas, table=table, euler=[bool(r) for r in table[:, 15].tolist()], cc=cc,
+        plan = dict(net_call=net_call, dedup=dedup, wver=wver, sigmas=sigmas, table=table, euler=[bool(r) for r in table[:, 15].tolist()], cc=cc,
                     step=torch.zeros(1, dtype=torch.int32, device=dev), x=torch.empty(x.shape, **f32),
                     noise=torch.empty(x.shape, **f32), x2=torch.empty(x.shape, **f32), x_euler=torch.empty(x.shape, **f32),
                     xin2=torch.empty((2 * B,) + tuple(x.shape[1:]), **f32), t2=torch.zeros(2 * B, dtype=torch.int64, device=dev),

@@ -39,6 +39,7 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
         self.use_cuda_graph = use_cuda_graph
         self._graphs: Dict[tuple, dict] = {}
         self._params = None
+        self._generation = 0            # bumped by invalidate(): step graphs captured by a sampler watch it too
 
     # ---- one network call, eager: a flat list of C-ABI kernel launches on the current stream ---------------------
     def _network(self, x, t, crossattn, control_hint, cond_feat):
@@ -149,7 +150,7 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
         call `invalidate()` after those."""
         if self._params is None:
             self._params = list(self.diffusion_model.parameters())
-        return sum(p._version for p in self._params) + sum(p.data_ptr() for p in self._params[:8])
+        return (sum(p._version for p in self._params) + sum(p.data_ptr() for p in self._params[:8]), self._generation)
 
     def reset_graphs(self):
         """Drop captured graphs (keeps the packed fp16 weights)."""
@@ -162,6 +163,7 @@ class OpenAIWrapperControlLDM3DTV2V(IdentityWrapper):
         call it themselves."""
         self._graphs.clear()
         self._params = None
+        self._generation += 1
         for m in self.diffusion_model.modules():
             if hasattr(m, "invalidate_packed"):
                 m.invalidate_packed()

@@ -132,3 +132,34 @@ def test_weight_edits_take_effect_under_graph_replay(gpu_wrappers):
         wrap.use_cuda_graph = True
         wrap.invalidate()
     assert torch.equal(wrap(x, t, cc), base)
+
+
+def test_weight_edits_reach_the_fused_sampler_step_graph(gpu_wrappers):
+    """The fused sampler replays ONE captured graph per step with the network calls inside; a LoRA merge between two
+    clips must drop it (the plan watches the wrapper's weight version / invalidate() generation)."""
+    from ccedit_b200 import checkpoint as ck
+    from ccedit_b200.sampling import BoundDenoiser, DiscreteDenoiser, FusedDPMPP2SAncestralSampler
+    g = load_golden("sampler_tv2v.pt")
+    B, T, h, w = g["shape"]
+    c, uc = oin.synthetic_cond(B, T, h, w, seed=7)
+    x0 = oin.synthetic_latent(B, T, h, w, seed=6)
+    wrap = gpu_wrappers("tv2v", graph=False)
+    sampler = FusedDPMPP2SAncestralSampler(num_steps=2, device="cuda", eta=0.0, s_noise=1.0, guider_config={
+        "target": "sgm.modules.diffusionmodules.guiders.VanillaCFGTV2V", "params": {"scale": 7.5}}, use_cuda_graph=True)
+    den = BoundDenoiser(DiscreteDenoiser().cuda(), wrap)
+    cd, ucd = _cuda(c), _cuda(uc)
+    base = sampler(den, x0.clone().cuda(), cd, uc=ucd)
+    assert torch.equal(sampler(den, x0.clone().cuda(), cd, uc=ucd), base)         # same plan, graph replay
+    key = "diffusion_model.output_blocks.5.1.transformer_blocks.0.attn2.to_q.weight"
+    p = dict(wrap.named_parameters())[key]
+    orig = p.detach().clone()
+    try:
+        lora = {"lora_unet_up_blocks_1_attentions_2_transformer_blocks_0_attn2_to_q.lora_down.weight": torch.randn(4, p.shape[1]) * 0.1,
+                "lora_unet_up_blocks_1_attentions_2_transformer_blocks_0_attn2_to_q.lora_up.weight": torch.randn(p.shape[0], 4) * 0.1}
+        assert ck.merge_lora(wrap, lora, alpha=0.8) == ["model." + key]
+        merged = sampler(den, x0.clone().cuda(), cd, uc=ucd)
+        assert not torch.equal(merged, base)
+    finally:
+        p.data.copy_(orig)
+        wrap.invalidate()
+    assert torch.equal(sampler(den, x0.clone().cuda(), cd, uc=ucd), base)

@@ -15,3 +15,4 @@ print({k:(v if not isinstance(v,list) else '...') for k,v in d['configs'].items(
 PY
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none --csv --log-file gpurun_out/traffic.csv python tools/one_call.py > gpurun_out/ncu_traffic.log 2>&1; echo "ncu traffic exit $?"; tail -2 gpurun_out/ncu_traffic.log
+timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref exit $?"; cut -c1-700 gpurun_out/bench_ref.json
