@@ -441,6 +441,311 @@ static int dispatch_ta(const __half* q, long long ldq, const __half* k, long lon
   return launch_ta<160, TK>(q, ldq, k, ldk, v, ldv, o, ldo, B, T, HW, heads, d, sl, st);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Attention over a SHORT key sequence shared by many query rows: the text cross-attention (77 keys per batch entry,
+// attention.py:444-448 with context = the CLIP tokens; 21 launches per network call).  q and o are the whole cost
+// (read 134 MB, write 134 MB at the top level for 0.03 TFLOP): the kernel is an HBM stream with a little tensor work
+// per row, and the long-sequence kernels - one (query tile, head) per pipeline pass - ran it at 1.2-1.6 TB/s.
+//   * a CTA owns one (key/value frame, head group) pair: the group's K and V columns ([lkv][G], G = heads_per_group * d
+//     <= 160 channels = 320 contiguous bytes per row) are staged in shared memory ONCE and stay there;
+//   * its warps walk the (query frame, 16-row block) units of that pair independently - no block-wide barrier in the
+//     loop: the unit's q rows arrive with 16-byte cp.async into a per-warp double buffer (the next unit's rows are in
+//     flight while this one is computed), S = Q K^T, the softmax and O = P V run on warp-level tensor-core MMAs
+//     (m16n8k16, everything in registers, one key "tile": no online rescaling), the output rows replace the query rows in
+//     the buffer and leave with 16-byte coalesced stores.
+// Shared-memory rows are G + 8 halves (odd multiple of 16 bytes): conflict-free ldmatrix.
+// ---------------------------------------------------------------------------------------------------------------
+struct SkParams {
+  const __half* q; long long ldq, q_fs;
+  __half* o; long long ldo, o_fs;
+  const __half* k; const __half* v;
+  long long ldk, ldv, kv_fs;
+  int lkv, kv_div, kv_mul, kv_add;
+  int frames, lq, d, hpg, ngroups, nkvf;
+  float scale_log2;
+};
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// first MMA of an accumulator chain: C = 0 comes from the zero register instead of 4 zeroed registers per n-tile
+__device__ __forceinline__ void mma_m16n8k16_first(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
+}
+
+// D: head dim (40 / 80 / 160: a head group is 160 / D heads = 160 channels, so every shared-memory offset below is an
+// immediate); NKT: 16-key groups (lkv in (16 NKT - 16, 16 NKT]: only the last two 8-key tiles can hold masked keys);
+// NW: warps per CTA (one CTA per SM: the warps are what hides the ldmatrix / HMMA / shuffle latencies of the per-head
+// chain - 12 while the accumulators leave room (14 warps cap the registers at 128: measured slower), 8 at d = 160).
+template <int D, int NKT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) short_kv_attn_kernel(const __grid_constant__ SkParams p) {
+  constexpr int HPG = 160 / D, G = HPG * D, RS = G + 8, CPR = G / 8;        // 20 16-byte chunks per row
+  constexpr int KSTEPS = (D + 15) / 16, NT_O = D / 8, NTK = 2 * NKT, KP = 16 * NKT;
+  constexpr bool kTail = (D % 16) != 0;                   // d % 16 == 8: the last k-step covers 8 foreign channels
+  constexpr int NJ = (16 * CPR + 31) / 32;                // 16-byte chunks of a unit per lane
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  __half* sK = reinterpret_cast<__half*>(sk_smem);         // [KP][RS]
+  __half* sV = sK + KP * RS;                               // [KP][RS]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* sQ = sV + KP * RS + warp * 2 * 16 * RS;          // this warp's [2][16][RS]
+
+  // (key/value frame, head group) pairs are dealt round-robin to the CTAs; the CTAs of a pair share its units
+  const int npairs = p.nkvf * p.ngroups;
+  const int pair = blockIdx.x % npairs;
+  const int sub = blockIdx.x / npairs, nsub = (gridDim.x - pair + npairs - 1) / npairs;   // CTAs working on this pair
+  const int kvi = pair / p.ngroups, grp = pair % p.ngroups;
+  const int f_begin = kvi * p.kv_div, f_end = min(p.frames, f_begin + p.kv_div);
+  const long long col0 = static_cast<long long>(grp) * G;
+  {
+    const long long kvf = static_cast<long long>(kvi) * p.kv_mul + p.kv_add;
+    const __half* kb = p.k + kvf * p.kv_fs + col0;
+    const __half* vb = p.v + kvf * p.kv_fs + col0;
+    for (int i = threadIdx.x; i < KP * CPR; i += NW * 32) {
+      const int r = i / CPR, c = i - r * CPR;
+      const bool ok = r < p.lkv;                           // rows lkv..KP-1: zero-filled (masked keys, finite V)
+      const long long rr = ok ? r : 0;
+      cp_async_16(smem_u32(sK + r * RS + c * 8), kb + rr * p.ldk + c * 8, ok);
+      cp_async_16(smem_u32(sV + r * RS + c * 8), vb + rr * p.ldv + c * 8, ok);
+    }
+    // the 8 padding halves of every row feed the last k-step / output group of the last head: keep them finite
+    for (int i = threadIdx.x; i < 2 * KP; i += NW * 32) *reinterpret_cast<uint4*>(sK + i * RS + G) = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < 2 * 16; i += 32) *reinterpret_cast<uint4*>(sQ + i * RS + G) = make_uint4(0, 0, 0, 0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+
+  // this lane's chunks of a unit: (row, 16-byte column) pairs, fixed for the whole kernel
+  int grow[NJ];                                            // row within the unit, -1 past the end
+  uint32_t soff[NJ];                                       // byte offset in the unit's buffer
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int i = lane + 32 * j, r = i / CPR, c = i - r * CPR;
+    grow[j] = i < 16 * CPR ? r : -1;
+    soff[j] = static_cast<uint32_t>(r * RS + c * 8) * 2u;
+  }
+  const int nrb = (p.lq + 15) >> 4;                        // 16-row blocks per frame
+  const int nunits = (f_end - f_begin) * nrb;              // < 2^31: frames * rows / 16
+  const int ustep = nsub * NW;
+  int uf0 = 0, uf1 = 0, ur0 = 0, ur1 = 0;                 // frame and first row of the unit in each buffer
+  const uint32_t sq_base = smem_u32(sQ);
+  auto stage = [&](int u, int buf) {                       // unit u -> this warp's buffer buf (one cp.async group)
+    if (u < nunits) {
+      const int fi = u / nrb;
+      const int f = f_begin + fi, r0 = (u - fi * nrb) << 4;
+      if (buf) { uf1 = f; ur1 = r0; } else { uf0 = f; ur0 = r0; }
+      const __half* qb = p.q + static_cast<long long>(f) * p.q_fs + col0;
+      const uint32_t dst = sq_base + buf * (16 * RS * 2);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (grow[j] >= 0) {
+          const int row = min(r0 + grow[j], p.lq - 1);     // rows past the end repeat the last row (never stored)
+          cp_async_16(dst + soff[j], qb + static_cast<long long>(row) * p.ldq + ((soff[j] >> 1) - grow[j] * RS), true);
+        }
+    }
+    cp_async_commit();
+  };
+  int u = sub * NW + warp;
+  stage(u, 0);
+  stage(u + ustep, 1);
+  const float c = p.scale_log2;
+  // per-lane ldmatrix byte offsets (row stride and head width are compile-time: the rest are instruction immediates)
+  const uint32_t q_lane = static_cast<uint32_t>((lane & 15) * RS + (lane >> 4) * 8) * 2u;
+  const uint32_t k_lane = smem_u32(sK) + static_cast<uint32_t>(((lane & 7) + ((lane >> 4) << 3)) * RS + ((lane >> 3) & 1) * 8) * 2u;
+  const uint32_t v_lane = smem_u32(sV) + static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * RS + (lane >> 4) * 8) * 2u;
+  const int ocol = (lane & 3) * 2;
+  int buf = 0;
+  for (; u < nunits; u += ustep, buf ^= 1) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint32_t bq = sq_base + buf * (16 * RS * 2);
+#pragma unroll 1
+    for (int h = 0; h < HPG; ++h) {
+      const uint32_t hq = bq + q_lane + h * (D * 2), hk = k_lane + h * (D * 2), hv = v_lane + h * (D * 2);
+      // ---- S = Q K^T: 16 query rows x KP keys ----
+      float sacc[NTK][4];
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        uint32_t qf[4];
+        ldmatrix_x4(qf, hq + ks * 32);
+        if (kTail && ks == KSTEPS - 1) qf[2] = qf[3] = 0u;        // zero the 8 channels past d
+#pragma unroll
+        for (int np = 0; np < NKT; ++np) {
+          uint32_t kf[4];
+          ldmatrix_x4(kf, hk + np * (16 * RS * 2) + ks * 32);
+          const uint32_t b0[2] = {kf[0], kf[1]}, b1[2] = {kf[2], kf[3]};
+          if (ks == 0) {
+            mma_m16n8k16_first(sacc[2 * np], qf, b0);
+            mma_m16n8k16_first(sacc[2 * np + 1], qf, b1);
+          } else {
+            mma_m16n8k16(sacc[2 * np], qf, b0);
+            mma_m16n8k16(sacc[2 * np + 1], qf, b1);
+          }
+        }
+      }
+      // ---- softmax over the lkv valid keys (rows g and g + 8 of the fragment); the scale (> 0) is applied inside the
+      //      exponential: 2^(s * c - max * c) ----
+#pragma unroll
+      for (int nt = NTK - 2; nt < NTK; ++nt) {
+        const int col = nt * 8 + ocol;
+        if (col >= p.lkv) sacc[nt][0] = sacc[nt][2] = -INFINITY;
+        if (col + 1 >= p.lkv) sacc[nt][1] = sacc[nt][3] = -INFINITY;
+      }
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < NTK; ++nt) {
+        mx[0] = fmaxf(mx[0], fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+        mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+      }
+      const float nm0 = -mx[0] * c, nm1 = -mx[1] * c;
+      float rs[2] = {0.f, 0.f};
+      uint32_t pf[NKT][4];
+#pragma unroll
+      for (int nt = 0; nt < NTK; ++nt) {
+        const float p0 = ex2_fast(fmaf(sacc[nt][0], c, nm0)), p1 = ex2_fast(fmaf(sacc[nt][1], c, nm0));
+        const float p2 = ex2_fast(fmaf(sacc[nt][2], c, nm1)), p3 = ex2_fast(fmaf(sacc[nt][3], c, nm1));
+        rs[0] += p0 + p1;
+        rs[1] += p2 + p3;
+        __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+        pf[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&h01);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&h23);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+        rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+      }
+      // ---- O = P V (the 8 columns past d of the last 16-column group are not computed) ----
+      float oacc[NT_O][4];
+#pragma unroll
+      for (int kk = 0; kk < NKT; ++kk) {
+#pragma unroll
+        for (int np = 0; np < (NT_O + 1) / 2; ++np) {
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, hv + kk * (16 * RS * 2) + np * 32);
+          const uint32_t b0[2] = {vf[0], vf[1]}, b1[2] = {vf[2], vf[3]};
+          if (kk == 0) {
+            mma_m16n8k16_first(oacc[2 * np], pf[kk], b0);
+            if (2 * np + 1 < NT_O) mma_m16n8k16_first(oacc[2 * np + 1], pf[kk], b1);
+          } else {
+            mma_m16n8k16(oacc[2 * np], pf[kk], b0);
+            if (2 * np + 1 < NT_O) mma_m16n8k16(oacc[2 * np + 1], pf[kk], b1);
+          }
+        }
+      }
+      const float inv0 = __fdividef(1.f, rs[0]), inv1 = __fdividef(1.f, rs[1]);
+      // the head's output rows replace its query rows in the buffer (Q of head h only feeds S of head h; the foreign
+      // channels its last k-step touched were zeroed in the fragment, not in memory)
+      __half* o0 = sQ + buf * (16 * RS) + (lane >> 2) * RS + h * D + ocol;
+      __half* o1 = o0 + 8 * RS;
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < NT_O; ++nt) {
+        *reinterpret_cast<__half2*>(o0 + nt * 8) = __floats2half2_rn(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+        *reinterpret_cast<__half2*>(o1 + nt * 8) = __floats2half2_rn(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+      }
+      __syncwarp();
+    }
+    {
+      const int f = buf ? uf1 : uf0, r0 = buf ? ur1 : ur0;
+      __half* ob = p.o + static_cast<long long>(f) * p.o_fs + col0;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(sQ) + buf * (16 * RS * 2);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (grow[j] >= 0 && r0 + grow[j] < p.lq)
+          *reinterpret_cast<uint4*>(ob + static_cast<long long>(r0 + grow[j]) * p.ldo + ((soff[j] >> 1) - grow[j] * RS)) =
+              *reinterpret_cast<const uint4*>(src + soff[j]);
+    }
+    __syncwarp();                                          // the buffer has been read: the unit after next may land in it
+    stage(u + 2 * ustep, buf);
+  }
+  cp_async_wait<0>();
+}
+
+template <int D>
+constexpr int sk_warps() { return D <= 80 ? 12 : 8; }
+
+template <int D, int NKT>
+static int launch_sk(const SkParams& p, int grid, cudaStream_t st) {
+  constexpr int NW = sk_warps<D>();
+  constexpr int RS = (160 / D) * D + 8;
+  const size_t smem = (static_cast<size_t>(2) * 16 * NKT + static_cast<size_t>(NW) * 2 * 16) * RS * 2;
+  if (smem > 227 * 1024) return -1;
+  static std::atomic<bool> attr_done[kMaxDevices];
+  const int dev = current_device();
+  CCEDIT_CHECK_ARG(dev >= 0, "ccedit_attention: no current CUDA device");
+  if (!attr_done[dev].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(short_kv_attn_kernel<D, NKT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_last_error("ccedit_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CCEDIT_ERR_CUDA;
+    }
+    attr_done[dev].store(true, std::memory_order_release);
+  }
+  short_kv_attn_kernel<D, NKT, NW><<<grid, NW * 32, smem, st>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_attention(short kv)");
+  return CCEDIT_OK;
+}
+
+// -> -1 when the problem is not of this kernel's kind (the caller goes on to the long-sequence kernels)
+static int attention_short_kv(const ccedit_attn_desc* a, cudaStream_t st) {
+  if (a->nseg != 1 || a->lkv[0] > 128 || a->kv_div[0] < 2) return -1;       // one short segment shared by >= 2 query frames
+  const int d = a->d;
+  if (d != 40 && d != 80 && d != 160) return -1;
+  const int hpg = 160 / d;                                               // a head group is 160 channels wide
+  if (a->heads % hpg != 0) return -1;
+  SkParams p;
+  memset(&p, 0, sizeof(p));
+  p.hpg = hpg;
+  p.ngroups = a->heads / hpg;
+  p.nkvf = (a->frames + a->kv_div[0] - 1) / a->kv_div[0];
+  const int sms = device_sm_count();
+  const int npairs = p.nkvf * p.ngroups;
+  if (sms <= 0 || npairs > sms) return -1;
+  // the rows must be worth a resident K/V copy per CTA
+  if (static_cast<long long>(a->frames) * a->lq < 1024) return -1;
+  p.q = static_cast<const __half*>(a->q);  p.ldq = a->ldq;  p.q_fs = a->q_frame_stride;
+  p.o = static_cast<__half*>(a->o);        p.ldo = a->ldo;  p.o_fs = a->o_frame_stride;
+  p.k = static_cast<const __half*>(a->k[0]);
+  p.v = static_cast<const __half*>(a->v[0]);
+  p.ldk = a->ldk[0];  p.ldv = a->ldv[0];  p.kv_fs = a->kv_frame_stride[0];
+  p.lkv = a->lkv[0];  p.kv_div = a->kv_div[0];  p.kv_mul = a->kv_mul[0];  p.kv_add = a->kv_add[0];
+  p.frames = a->frames;  p.lq = a->lq;  p.d = d;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  if ((reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.o) | reinterpret_cast<uintptr_t>(p.k) |
+       reinterpret_cast<uintptr_t>(p.v)) & 15) return -1;
+  const int nkt = (p.lkv + 15) / 16;
+  // every pair gets the same number of CTAs
+  const int grid = (sms / npairs) * npairs;
+#define CCEDIT_SK(DP_)                                                            \
+  switch (nkt) {                                                                  \
+    case 1: return launch_sk<DP_, 1>(p, grid, st);                          \
+    case 2: return launch_sk<DP_, 2>(p, grid, st);                          \
+    case 3: return launch_sk<DP_, 3>(p, grid, st);                          \
+    case 4: return launch_sk<DP_, 4>(p, grid, st);                          \
+    case 5: return launch_sk<DP_, 5>(p, grid, st);                          \
+    case 6: return launch_sk<DP_, 6>(p, grid, st);                          \
+    case 7: return launch_sk<DP_, 7>(p, grid, st);                          \
+    default: return launch_sk<DP_, 8>(p, grid, st);                         \
+  }
+  if (d == 40) { CCEDIT_SK(40) }
+  if (d == 80) { CCEDIT_SK(80) }
+  CCEDIT_SK(160)
+#undef CCEDIT_SK
+}
+
 }  // namespace ccedit
 
 using namespace ccedit;
@@ -482,6 +787,11 @@ extern "C" int ccedit_attention(const ccedit_attn_desc* a, void* stream) {
   // head dims up to 64 (d = 40: 88 % of the attention FLOPs) run on tcgen05 / TMEM; CCEDIT_ATTN_LEGACY=1 forces the
   // mma.sync kernel (A/B measurements only)
   static const bool legacy = [] { const char* e = getenv("CCEDIT_ATTN_LEGACY"); return e && e[0] == '1'; }();
+  static const bool no_short = [] { const char* e = getenv("CCEDIT_ATTN_SHORT"); return e && e[0] == '0'; }();
+  if (!legacy && !no_short && a->scale > 0.f) {             // a short key sequence shared by many rows: HBM stream of q and o
+    const int rc = attention_short_kv(a, st);
+    if (rc >= 0) return rc;
+  }
   if (!legacy && (reinterpret_cast<uintptr_t>(a->q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0 &&
       a->scale > 0.f) {
     const int rc = attention_tc(a, st);

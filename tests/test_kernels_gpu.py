@@ -305,17 +305,46 @@ def test_attention_text_keys_shared_by_frames(ops):
     close(out, ref, "text attention", atol=ATOL_ATTN)
 
 
-@pytest.mark.parametrize("B,T,L,heads,d", [(2, 17, 6144, 8, 40), (2, 17, 1536, 8, 80), (2, 9, 2000, 8, 40)])
-def test_attention_text_keys_many_heads_per_cta(ops, B, T, L, heads, d):
-    """Text cross-attention at the sizes of the network call: with one or two key tiles per head and enough query tiles
-    the kernel takes several heads per CTA in a row (flash_attn_tc2_kernel<.., MH = true>: next-head Q prefetch, per-head
-    statistics reset, O re-initialised by the first P.V) - 8 heads per CTA at L0, 2 at L1."""
+@pytest.mark.parametrize("B,T,L,Lkv,heads,d", [(2, 17, 6144, 77, 8, 40), (2, 17, 1536, 77, 8, 80), (2, 17, 384, 77, 8, 160),
+                                               (2, 17, 96, 77, 8, 160), (2, 9, 2001, 77, 8, 40), (3, 5, 333, 128, 8, 80),
+                                               (2, 33, 50, 1, 8, 40), (1, 64, 100, 16, 4, 40), (2, 8, 130, 100, 2, 160)])
+def test_attention_short_keys_shared_by_frames(ops, B, T, L, Lkv, heads, d):
+    """Text cross-attention at the sizes of the network call (and ragged ones): <= 128 keys shared by the T frames of a
+    batch entry take short_kv_attn_kernel - K / V of a head group resident in shared memory, per-warp streaming of the
+    query rows (attention.cu); partial last row block, 1 / 16 / 128 keys, 1 / 2 / 4 heads per group."""
     C = heads * d
-    q, k, v = rnd(B * T, L, C, seed=57), rnd(B, 77, C, seed=58), rnd(B, 77, C, seed=59)
+    q, k, v = rnd(B * T, L, C, seed=57), rnd(B, Lkv, C, seed=58), rnd(B, Lkv, C, seed=59)
     out = torch.empty(B * T, L, C, dtype=torch.float16, device="cuda")
     ops.attention(q.cuda(), [ops.KVSegment(k.cuda(), v.cuda(), div=T)], heads, out)
     ref = _sdpa(q, k.repeat_interleave(T, 0), v.repeat_interleave(T, 0), heads)
-    close(out, ref, f"text attention, several heads per CTA (L={L}, d={d})", atol=ATOL_ATTN)
+    close(out, ref, f"text attention, short keys (L={L}, Lkv={Lkv}, d={d})", atol=ATOL_ATTN)
+
+
+def test_attention_short_keys_strided_views_and_ragged_frames(ops):
+    """q and the output as column slices of wider buffers (fused q|k|v projection layout), k / v as slices of one [.., 2C]
+    projection, and a frame count that is not a multiple of the frames per key set (the last set serves fewer frames)."""
+    Fr, div, L, Lkv, heads, d = 7, 3, 400, 77, 8, 40
+    C = heads * d
+    qkv, kv = rnd(Fr, L, 3 * C, seed=71).cuda(), rnd(3, Lkv, 2 * C, seed=72).cuda()
+    buf = torch.zeros(Fr, L, 2 * C, dtype=torch.float16, device="cuda")
+    q, k, v, out = qkv[..., C:2 * C], kv[..., :C], kv[..., C:], buf[..., C:]
+    ops.attention(q, [ops.KVSegment(k, v, div=div)], heads, out)
+    idx = torch.arange(Fr) // div
+    ref = _sdpa(q.cpu().contiguous(), k.cpu()[idx].contiguous(), v.cpu()[idx].contiguous(), heads)
+    close(out, ref, "text attention on strided views", atol=ATOL_ATTN)
+    assert torch.count_nonzero(buf[..., :C]) == 0, "columns outside the output view were written"
+
+
+@pytest.mark.parametrize("Fr,L,heads,d", [(120, 200, 8, 40), (450, 200, 8, 40)])
+def test_attention_many_heads_per_cta(ops, Fr, L, heads, d):
+    """One or two key tiles per head and enough query tiles: flash_attn_tc2_kernel takes several heads per CTA in a row
+    (MH = true: next-head Q prefetch, per-head statistics reset, O re-initialised by the first P.V) - 2 and 8 heads per
+    CTA here (per-frame keys, so the short-key kernel does not apply)."""
+    C = heads * d
+    q, k, v = rnd(Fr, L, C, seed=61), rnd(Fr, L, C, seed=62), rnd(Fr, L, C, seed=63)
+    out = torch.empty(Fr, L, C, dtype=torch.float16, device="cuda")
+    ops.attention(q.cuda(), [ops.KVSegment(k.cuda(), v.cuda())], heads, out)
+    close(out, _sdpa(q, k, v, heads), f"attention, several heads per CTA (F={Fr}, L={L})", atol=ATOL_ATTN)
 
 
 def test_attention_center_self_two_segments(ops):
