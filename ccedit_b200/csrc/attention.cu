@@ -249,6 +249,19 @@ static int launch_fa(const FaParams& p, int frames, int heads, cudaStream_t st) 
   return CCEDIT_OK;
 }
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// first MMA of an accumulator chain: C = 0 comes from the zero register instead of 4 zeroed registers per n-tile
+__device__ __forceinline__ void mma_m16n8k16_first(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // temporal attention: one CTA per pixel (x head group), one warp per head.
 //   phase 1: the CTA streams the pixel's q, k, v rows ([T][C], C = heads*d contiguous) into shared memory with
@@ -429,6 +442,209 @@ static int launch_ta(const __half* q, long long ldq, const __half* k, long long 
   return CCEDIT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same operator for the shapes of the network (8 heads, d = 40 / 80 / 160, T = 9 / 17 / 33 keyframes) with everything
+// a compile-time constant.  ncu of the generic kernel above at the top level (2 x 6144 pixels, T = 17, d = 40): 1 236 warp
+// instructions per (pixel, head) for 48 HMMA, issue slots 74 % busy - not the HBM stream bounds it but index arithmetic
+// on run-time strides, per-score masks and selects, exp2f's range handling, the zeroing of accumulators and whole MMAs on
+// key tiles that hold no key.  Here: HPB heads per CTA (one warp each), row stride and head offset are immediates of the
+// ldmatrix instructions, the T - 1 clamp of the fragment rows is six per-lane offsets computed once, only the key
+// tile that straddles T is masked, key tiles past T are not multiplied at all, the scale lives in the exponent
+// (2^(s c - max c), ex2.approx), the first MMA of a chain takes C = 0 from the zero register.
+// ---------------------------------------------------------------------------------------------------------------
+template <int D, int T, int HPB>
+__global__ void __launch_bounds__(HPB * 32) temporal_attn_fixed_kernel(const __half* __restrict__ q, long long ldq,
+                                                                       const __half* __restrict__ k, long long ldk,
+                                                                       const __half* __restrict__ v, long long ldv,
+                                                                       __half* __restrict__ o, long long ldo, int HW,
+                                                                       float scale_log2) {
+  constexpr int C = HPB * D, RS = C + 8, CPR = C / 8;
+  constexpr int MB = (T + 15) / 16, NT = (T + 7) / 8, NP = (NT + 1) / 2, KK = (T + 15) / 16;
+  constexpr int KSTEPS = (D + 15) / 16, NT_O = D / 8;
+  constexpr bool kTail = (D % 16) != 0;
+  extern __shared__ __align__(16) uint8_t ta_smem[];
+  __half* sq = reinterpret_cast<__half*>(ta_smem);        // [T][RS]; k and v follow
+  __half* sk = sq + T * RS;
+  __half* sv = sk + T * RS;
+  const long long col0 = static_cast<long long>(blockIdx.y) * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pix = blockIdx.x;                       // b*HW + hw
+  const long long row0 = (pix / HW) * T * HW + pix % HW;  // row of frame 0; frame t adds t*HW
+  for (int i = threadIdx.x; i < T * CPR; i += HPB * 32) {
+    const int t = i / CPR, c = i - t * CPR;
+    const long long row = row0 + static_cast<long long>(t) * HW;
+    const uint32_t dst = static_cast<uint32_t>(t * RS + c * 8) * 2u;
+    cp_async_16(smem_u32(sq) + dst, q + row * ldq + col0 + c * 8, true);
+    cp_async_16(smem_u32(sk) + dst, k + row * ldk + col0 + c * 8, true);
+    cp_async_16(smem_u32(sv) + dst, v + row * ldv + col0 + c * 8, true);
+  }
+  // the 8 padding halves at the end of every row feed the last k-step of the last head: keep them finite
+  for (int i = threadIdx.x; i < 3 * T; i += HPB * 32) *reinterpret_cast<uint4*>(sq + i * RS + C) = make_uint4(0, 0, 0, 0);
+  cp_async_commit();
+  // fragment rows past T - 1 alias frame T - 1 (masked keys / never-stored query rows): per-lane byte offsets, once
+  uint32_t qrow[MB], krow[NP], vrow[KK];
+#pragma unroll
+  for (int i = 0; i < MB; ++i) qrow[i] = static_cast<uint32_t>(min(i * 16 + (lane & 15), T - 1) * RS + (lane >> 4) * 8) * 2u;
+#pragma unroll
+  for (int i = 0; i < NP; ++i)
+    krow[i] = static_cast<uint32_t>(min(i * 16 + (lane & 7) + ((lane >> 4) << 3), T - 1) * RS + ((lane >> 3) & 1) * 8) * 2u;
+#pragma unroll
+  for (int i = 0; i < KK; ++i)
+    vrow[i] = static_cast<uint32_t>(min(i * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, T - 1) * RS + (lane >> 4) * 8) * 2u;
+  const uint32_t hq = smem_u32(sq) + warp * (D * 2), hk = smem_u32(sk) + warp * (D * 2), hv = smem_u32(sv) + warp * (D * 2);
+  const int ocol = (lane & 3) * 2;
+  const float c = scale_log2;
+  cp_async_wait<0>();
+  __syncthreads();
+
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) {
+    // ---- S = Q K^T for 16 query frames x the NT key tiles that hold a key ----
+    float sacc[NT][4];
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      uint32_t qf[4];
+      ldmatrix_x4(qf, hq + qrow[mb] + ks * 32);
+      if (kTail && ks == KSTEPS - 1) qf[2] = qf[3] = 0u;           // zero the 8 channels past d
+#pragma unroll
+      for (int np = 0; np < NP; ++np) {
+        uint32_t kf[4];
+        ldmatrix_x4(kf, hk + krow[np] + ks * 32);
+        const uint32_t b0[2] = {kf[0], kf[1]}, b1[2] = {kf[2], kf[3]};
+        if (ks == 0) {
+          mma_m16n8k16_first(sacc[2 * np], qf, b0);
+          if (2 * np + 1 < NT) mma_m16n8k16_first(sacc[2 * np + 1], qf, b1);
+        } else {
+          mma_m16n8k16(sacc[2 * np], qf, b0);
+          if (2 * np + 1 < NT) mma_m16n8k16(sacc[2 * np + 1], qf, b1);
+        }
+      }
+    }
+    // ---- softmax over the T keys (rows g and g + 8 of the fragment) ----
+    if (T % 8 != 0) {
+      const int col = (NT - 1) * 8 + ocol;
+      if (col >= T) sacc[NT - 1][0] = sacc[NT - 1][2] = -INFINITY;
+      if (col + 1 >= T) sacc[NT - 1][1] = sacc[NT - 1][3] = -INFINITY;
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(sacc[nt][0], sacc[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+      mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+    }
+    const float nm0 = -mx[0] * c, nm1 = -mx[1] * c;
+    float rs[2] = {0.f, 0.f};
+    uint32_t pf[KK][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * KK; ++nt) {
+      if (nt < NT) {
+        const float p0 = ex2_fast(fmaf(sacc[nt][0], c, nm0)), p1 = ex2_fast(fmaf(sacc[nt][1], c, nm0));
+        const float p2 = ex2_fast(fmaf(sacc[nt][2], c, nm1)), p3 = ex2_fast(fmaf(sacc[nt][3], c, nm1));
+        rs[0] += p0 + p1;
+        rs[1] += p2 + p3;
+        __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+        pf[nt >> 1][(nt & 1) * 2 + 0] = *reinterpret_cast<uint32_t*>(&h01);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&h23);
+      } else {                                                     // the key tile past T inside the last 16-key step
+        pf[nt >> 1][(nt & 1) * 2 + 0] = 0u;
+        pf[nt >> 1][(nt & 1) * 2 + 1] = 0u;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+      rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+    }
+    // ---- O = P V (the 8 columns past d of the last 16-column group are not computed) ----
+    float oacc[NT_O][4];
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+#pragma unroll
+      for (int np = 0; np < (NT_O + 1) / 2; ++np) {
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, hv + vrow[kk] + np * 32);
+        const uint32_t b0[2] = {vf[0], vf[1]}, b1[2] = {vf[2], vf[3]};
+        if (kk == 0) {
+          mma_m16n8k16_first(oacc[2 * np], pf[kk], b0);
+          if (2 * np + 1 < NT_O) mma_m16n8k16_first(oacc[2 * np + 1], pf[kk], b1);
+        } else {
+          mma_m16n8k16(oacc[2 * np], pf[kk], b0);
+          if (2 * np + 1 < NT_O) mma_m16n8k16(oacc[2 * np + 1], pf[kk], b1);
+        }
+      }
+    }
+    const float inv0 = __fdividef(1.f, rs[0]), inv1 = __fdividef(1.f, rs[1]);
+    // the output rows of this head replace its query rows (Q of block mb only feeds S of block mb; a later block's
+    // clamped rows read frame T - 1, which belongs to the last block)
+    const int r0 = mb * 16 + (lane >> 2), r1 = r0 + 8;
+    __half* o0 = sq + r0 * RS + warp * D + ocol;
+    __half* o1 = o0 + 8 * RS;
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < NT_O; ++nt) {
+      if (r0 < T) *reinterpret_cast<__half2*>(o0 + nt * 8) = __floats2half2_rn(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+      if (r1 < T) *reinterpret_cast<__half2*>(o1 + nt * 8) = __floats2half2_rn(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * CPR; i += HPB * 32) {
+    const int t = i / CPR, cc = i - t * CPR;
+    *reinterpret_cast<uint4*>(o + (row0 + static_cast<long long>(t) * HW) * ldo + col0 + cc * 8) =
+        *reinterpret_cast<const uint4*>(sq + t * RS + cc * 8);
+  }
+}
+
+template <int D, int T, int HPB>
+static int launch_ta_fixed(const __half* q, long long ldq, const __half* k, long long ldk, const __half* v, long long ldv,
+                           __half* o, long long ldo, int B, int HW, int heads, float scale_log2, cudaStream_t st) {
+  constexpr size_t smem = static_cast<size_t>(3) * T * (HPB * D + 8) * 2;
+  static_assert(smem <= 227 * 1024, "temporal_attn_fixed_kernel: shared memory");
+  static std::atomic<bool> attr_done[kMaxDevices];
+  const int dev = current_device();
+  CCEDIT_CHECK_ARG(dev >= 0, "ccedit_temporal_attention: no current CUDA device");
+  if (!attr_done[dev].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(temporal_attn_fixed_kernel<D, T, HPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_last_error("ccedit_temporal_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return CCEDIT_ERR_CUDA;
+    }
+    attr_done[dev].store(true, std::memory_order_release);
+  }
+  const dim3 grid(static_cast<unsigned>(static_cast<long long>(B) * HW), heads / HPB);
+  temporal_attn_fixed_kernel<D, T, HPB><<<grid, HPB * 32, smem, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, HW, scale_log2);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  CCEDIT_CUDA_LAUNCH_CHECK("ccedit_temporal_attention");
+  return CCEDIT_OK;
+}
+
+// the network's shapes -> the specialised kernel; -1 = not one of them (generic kernel)
+static int dispatch_ta_fixed(const __half* q, long long ldq, const __half* k, long long ldk, const __half* v, long long ldv,
+                             __half* o, long long ldo, int B, int T, int HW, int heads, int d, float sl, cudaStream_t st) {
+  static const bool off = [] { const char* e = getenv("CCEDIT_TA_FIXED"); return e && e[0] == '0'; }();
+  if (off || heads != 8) return -1;
+#define CCEDIT_TAF(D_, T_, H_) return launch_ta_fixed<D_, T_, H_>(q, ldq, k, ldk, v, ldv, o, ldo, B, HW, heads, sl, st);
+  if (d == 40) {      // heads per CTA: all 8 while three CTAs per SM fit (<= 72 KB), else the largest group that does
+    if (T == 9) CCEDIT_TAF(40, 9, 8)
+    if (T == 17) CCEDIT_TAF(40, 17, 8)
+    if (T == 33) CCEDIT_TAF(40, 33, 8)
+  } else if (d == 80) {
+    if (T == 9) CCEDIT_TAF(80, 9, 8)
+    if (T == 17) CCEDIT_TAF(80, 17, 8)
+    if (T == 33) CCEDIT_TAF(80, 33, 4)
+  } else if (d == 160) {
+    if (T == 9) CCEDIT_TAF(160, 9, 8)
+    if (T == 17) CCEDIT_TAF(160, 17, 4)
+    if (T == 33) CCEDIT_TAF(160, 33, 2)
+  }
+#undef CCEDIT_TAF
+  return -1;
+}
+
 template <int TK>
 static int dispatch_ta(const __half* q, long long ldq, const __half* k, long long ldk, const __half* v, long long ldv,
                        __half* o, long long ldo, int B, int T, int HW, int heads, int d, float sl, cudaStream_t st) {
@@ -465,19 +681,6 @@ struct SkParams {
   int frames, lq, d, hpg, ngroups, nkvf;
   float scale_log2;
 };
-
-__device__ __forceinline__ float ex2_fast(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// first MMA of an accumulator chain: C = 0 comes from the zero register instead of 4 zeroed registers per n-tile
-__device__ __forceinline__ void mma_m16n8k16_first(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
-}
 
 // D: head dim (40 / 80 / 160: a head group is 160 / D heads = 160 channels, so every shared-memory offset below is an
 // immediate); NKT: 16-key groups (lkv in (16 NKT - 16, 16 NKT]: only the last two 8-key tiles can hold masked keys);
@@ -824,6 +1027,10 @@ extern "C" int ccedit_temporal_attention(const void* q, int64_t ldq, const void*
   __half* op = static_cast<__half*>(o);
   const float sl = scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (scale > 0.f) {
+    const int rc = dispatch_ta_fixed(qp, ldq, kp, ldk, vp, ldv, op, ldo, B, T, HW, heads, d, sl, st);
+    if (rc >= 0) return rc;
+  }
   if (T <= 32) return dispatch_ta<32>(qp, ldq, kp, ldk, vp, ldv, op, ldo, B, T, HW, heads, d, sl, st);
   return dispatch_ta<64>(qp, ldq, kp, ldk, vp, ldv, op, ldo, B, T, HW, heads, d, sl, st);
 }

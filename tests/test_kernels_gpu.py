@@ -361,7 +361,10 @@ def test_attention_center_self_two_segments(ops):
 
 
 @pytest.mark.parametrize("B,T,HW,heads,d", [(2, 17, 50, 8, 40), (1, 9, 30, 8, 160), (2, 33, 20, 8, 80), (1, 1, 5, 8, 40),
-                                           (1, 33, 6, 8, 160), (1, 40, 3, 4, 16), (1, 17, 9, 4, 96), (2, 16, 11, 8, 24), (1, 64, 2, 8, 40)])
+                                           (1, 33, 6, 8, 160), (1, 40, 3, 4, 16), (1, 17, 9, 4, 96), (2, 16, 11, 8, 24), (1, 64, 2, 8, 40),
+                                           # the nine (d, T) pairs of the network and its sweep: temporal_attn_fixed_kernel
+                                           (2, 9, 37, 8, 40), (1, 33, 21, 8, 40), (2, 9, 13, 8, 80), (2, 17, 29, 8, 80),
+                                           (2, 17, 19, 8, 160)])
 def test_temporal_attention(ops, B, T, HW, heads, d):
     C = heads * d
     q, k, v = rnd(B, T, HW, C, seed=33), rnd(B, T, HW, C, seed=34), rnd(B, T, HW, C, seed=35)
