@@ -48,8 +48,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-// SiLU with the fast-division intrinsic (MUFU.RCP + FMUL, ~2 ulp): the IEEE '/' drags a slow-path call into every use
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU as x * rcp(1 + 2^(-x log2 e)) on the two approximate MUFU ops (~2 ulp): 5 instructions.  The IEEE '/' drags a
+// slow-path call into every use, and __fdividef adds a range fix-up (FSETP + 2 FMUL) for denominators above 2^126 that
+// 1 + e^-x only reaches where the result is 0 either way (ncu of the GroupNorm kernels: FMUL 21 % of all instructions).
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 // exact-erf GELU (torch F.gelu default, reference attention.py:120-122): gelu(x) = x * Phi(x).
 // Phi(-|x|) = exp2(q(-|x|)) with q a degree-6 minimax fit of log2(Phi) on [-5.5, 0] (Lawson iteration, tools/fit_gelu.py):
 // relative error of Phi <= 2.7e-5 INCLUDING the left tail (the erf form 0.5*(1+erf) cancels there), max |gelu error|

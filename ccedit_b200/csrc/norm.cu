@@ -292,7 +292,7 @@ __global__ void gn_spatial_fused_kernel(const __half* __restrict__ x, __half* __
   for (; r - 3 * rpi >= row_begin; r -= 4 * rpi) {
     uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldcg(xb + static_cast<size_t>(r - k * rpi) * nvec);
+    for (int k = 0; k < 4; ++k) u[k] = __ldlu(xb + static_cast<size_t>(r - k * rpi) * nvec);   // last use: the line may leave L2
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float v[8];
@@ -302,18 +302,18 @@ __global__ void gn_spatial_fused_kernel(const __half* __restrict__ x, __half* __
         float t = v[j] * sc[j] + sh[j];
         v[j] = silu ? silu_f(t) : t;
       }
-      yb[static_cast<size_t>(r - k * rpi) * nvec] = pack8(v);
+      __stcs(yb + static_cast<size_t>(r - k * rpi) * nvec, pack8(v));   // streaming store: y must not push the slices still to be re-read out of L2
     }
   }
   for (; r >= row_begin; r -= rpi) {
     float v[8];
-    unpack8(__ldcg(xb + static_cast<size_t>(r) * nvec), v);
+    unpack8(__ldlu(xb + static_cast<size_t>(r) * nvec), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float t = v[j] * sc[j] + sh[j];
       v[j] = silu ? silu_f(t) : t;
     }
-    yb[static_cast<size_t>(r) * nvec] = pack8(v);
+    __stcs(yb + static_cast<size_t>(r) * nvec, pack8(v));
   }
 }
 
@@ -410,7 +410,7 @@ __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restr
           float u = v[j] * sc[j] + sh[j];
           v[j] = silu ? silu_f(u) : u;
         }
-        yb[(t + k) * tstride] = pack8(v);
+        __stcs(yb + (t + k) * tstride, pack8(v));        // streaming: y is not read again by this kernel
       }
     }
     for (; t < T; ++t) {
@@ -421,7 +421,7 @@ __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restr
         float u = v[j] * sc[j] + sh[j];
         v[j] = silu ? silu_f(u) : u;
       }
-      yb[t * tstride] = pack8(v);
+      __stcs(yb + t * tstride, pack8(v));
     }
   }
 }
