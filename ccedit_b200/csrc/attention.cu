@@ -317,7 +317,6 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
 
   const bool mask_tail = (d & 15) != 0;                   // d % 16 == 8: the last k-step covers 8 foreign channels
   for (int head = warp; head < heads; head += (blockDim.x >> 5)) {
-    const __half* hq = sq + head * d;
     const __half* hk = sk + head * d;
     const __half* hv = sv + head * d;
     for (int m0 = 0; m0 < T; m0 += 16) {
@@ -329,8 +328,11 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const __half* __rest
       for (int ks = 0; ks < KSTEPS; ++ks) {
         if (ks * 16 >= d) break;                                   // DP may exceed d by whole k-steps (e.g. d = 96)
         uint32_t qf[4];
-        ldmatrix_x4(qf, smem_u32(hq + min(m0 + (lane & 15), tl) * RS + ks * 16 + (lane >> 4) * 8));
-        if (mask_tail && d - ks * 16 == 8) qf[2] = qf[3] = 0u;     // zero the 8 channels past d
+        // d % 16 == 8: the upper half of the last k-step lies past d - in the next head's columns, which that head's warp
+        // may be overwriting with its output rows.  Those lanes read the row's zero padding instead (no race, no select).
+        const __half* qrow_p = sq + min(m0 + (lane & 15), tl) * RS;
+        const bool past = mask_tail && d - ks * 16 == 8 && lane >= 16;
+        ldmatrix_x4(qf, smem_u32(past ? qrow_p + C : qrow_p + head * d + ks * 16 + (lane >> 4) * 8));
 #pragma unroll
         for (int np = 0; np < NTK / 2; ++np) {
           uint32_t kf[4];
@@ -504,8 +506,10 @@ __global__ void __launch_bounds__(HPB * 32) temporal_attn_fixed_kernel(const __h
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks) {
       uint32_t qf[4];
-      ldmatrix_x4(qf, hq + qrow[mb] + ks * 32);
-      if (kTail && ks == KSTEPS - 1) qf[2] = qf[3] = 0u;           // zero the 8 channels past d
+      // d % 16 == 8: the upper half of the last k-step lies past d, in the next head's columns (which that head's warp may
+      // be overwriting with its output rows): those lanes read the zero padding at the end of the row instead
+      const bool past = kTail && ks == KSTEPS - 1 && lane >= 16;
+      ldmatrix_x4(qf, past ? smem_u32(sq) + qrow[mb] - 16 + C * 2 : hq + qrow[mb] + ks * 32);
 #pragma unroll
       for (int np = 0; np < NP; ++np) {
         uint32_t kf[4];
