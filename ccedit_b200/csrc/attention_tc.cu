@@ -193,9 +193,15 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   uint8_t* sQ = smem;                                    // [NB][128][128 B]
   uint8_t* sKV = smem + Cfg::QBytes;                     // stages x (K [NB][KT][128 B], V [NB][KT][128 B])
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kT2Stages * 2 * Cfg::KBytes);
-  uint64_t* kv_full = bars;                              // [stages]
-  uint64_t* kv_empty = bars + kT2Stages;                 // [stages]
-  uint64_t* s_full = bars + 2 * kT2Stages;               // S ready
+  // K and V tiles have their own full / empty barriers: K(j) is released by Q K_j^T, a whole softmax earlier than P V_j
+  // releases V(j), so that the next-but-one K tile is in flight a tile earlier.  With one barrier per stage the K load was
+  // requested only ~0.1 tile periods before it was needed - hidden at d = 40 (128-key tiles, long softmax), but at
+  // d = 80 / 160 (64-key tiles) the softmax warps waited ~a TMA latency per tile for S (ncu: long_scoreboard 3.3).
+  uint64_t* k_full = bars;                               // [stages]
+  uint64_t* v_full = bars + kT2Stages;                   // [stages]
+  uint64_t* k_empty = bars + 2 * kT2Stages;              // [stages]
+  uint64_t* v_empty = bars + 3 * kT2Stages;              // [stages]
+  uint64_t* s_full = bars + 4 * kT2Stages;               // S ready
   uint64_t* p_full = s_full + 1;                         // P written (256 arrivals)
   uint64_t* q_full = p_full + 1;                         // Q tile in shared memory (128 arrivals)
   uint64_t* s_free = q_full + 1;                         // S is in registers (256 arrivals)
@@ -215,8 +221,10 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     tma_prefetch_desc(&tmK0);
     tma_prefetch_desc(&tmV0);
     for (int s = 0; s < kT2Stages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(p_full, 256);
@@ -235,27 +243,37 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < total; ++it) {
+    // ===================== TMA producer: two cursors, K runs ahead of V =====================
+    int kst = 0, vst = 0, kit = 0, vit = 0;
+    uint32_t kph = 0, vph = 0;
+    auto issue = [&](int it, int stage, bool is_v) {
       const int hl = MH ? it / ntiles : 0, j = it - hl * ntiles;
       const int head = head0 + hl;
       const int seg = j < p.ntile[0] ? 0 : 1;
       const int k0 = (seg == 0 ? j : j - p.ntile[0]) * KT;
       const int kvf = (f / p.kv_div[seg]) * p.kv_mul[seg] + p.kv_add[seg];
-      mbar_wait(&kv_empty[stage], phase ^ 1u);
-      uint8_t* sK = sKV + stage * 2 * Cfg::KBytes;
-      mbar_arrive_expect_tx_warp(&kv_full[stage], 2u * Cfg::KBytes);
+      uint8_t* dst = sKV + stage * 2 * Cfg::KBytes + (is_v ? Cfg::KBytes : 0);
+      uint64_t* bar = is_v ? &v_full[stage] : &k_full[stage];
+      const CUtensorMap* tm = is_v ? (seg == 0 ? &tmV0 : &tmV1) : (seg == 0 ? &tmK0 : &tmK1);
+      mbar_arrive_expect_tx_warp(bar, static_cast<uint32_t>(Cfg::KBytes));
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        tma_load_3d_warp(sK + b * KT * 128, seg == 0 ? &tmK0 : &tmK1, &kv_full[stage], head * d + 64 * b, k0, kvf);
-        tma_load_3d_warp(sK + Cfg::KBytes + b * KT * 128, seg == 0 ? &tmV0 : &tmV1, &kv_full[stage], head * d + 64 * b, k0, kvf);
+      for (int b = 0; b < NB; ++b) tma_load_3d_warp(dst + b * KT * 128, tm, bar, head * d + 64 * b, k0, kvf);
+    };
+    while (kit < total || vit < total) {
+      bool moved = false;
+      if (kit < total && mbar_test_wait(&k_empty[kst], kph ^ 1u)) {
+        issue(kit, kst, false);
+        ++kit;
+        if (++kst == kT2Stages) { kst = 0; kph ^= 1u; }
+        moved = true;
       }
-      if (++stage == kT2Stages) {
-        stage = 0;
-        phase ^= 1u;
+      if (vit < total && mbar_test_wait(&v_empty[vst], vph ^ 1u)) {
+        issue(vit, vst, true);
+        ++vit;
+        if (++vst == kT2Stages) { vst = 0; vph ^= 1u; }
+        moved = true;
       }
+      if (!moved) __nanosleep(32);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -266,7 +284,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
     mbar_wait(q_full, 0);
     fence_proxy_async_smem();
     tcgen05_fence_after();
-    mbar_wait(&kv_full[0], 0);
+    mbar_wait(&k_full[0], 0);
     tcgen05_fence_after();
     {
       const uint32_t sKa = smem_u32(sKV);
@@ -275,6 +293,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa + (ks >> 2) * (kTcTile * 128)) + 2u * (ks & 3),
                          umma_desc_k_sw128(sKa + (ks >> 2) * (KT * 128)) + 2u * (ks & 3), idesc_s, ks ? 1u : 0u);
       umma_commit_warp(s_full);
+      umma_commit_warp(&k_empty[0]);                      // K(0) is free as soon as these MMAs have read it
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -289,7 +308,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
       }
       auto next_scores = [&]() {                         // S(it+1) = Q K^T: S is free once it sits in registers
         if (it + 1 >= total) return;
-        mbar_wait(&kv_full[nstage], nphase);
+        mbar_wait(&k_full[nstage], nphase);
         mbar_wait(s_free, static_cast<uint32_t>(it & 1));
         if (MH && last_tile) {                           // first key tile of the next head: its Q tile must have landed
           mbar_wait(q_full, static_cast<uint32_t>((hl + 1) & 1));
@@ -302,12 +321,14 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
           umma_f16_ss_warp(tS, umma_desc_k_sw128(sQa + (ks >> 2) * (kTcTile * 128)) + 2u * (ks & 3),
                            umma_desc_k_sw128(sKa + (ks >> 2) * (KT * 128)) + 2u * (ks & 3), idesc_s, ks ? 1u : 0u);
         umma_commit_warp(s_full);
+        umma_commit_warp(&k_empty[nstage]);
       };
       // within a head the next scores go first (they are ready long before P); across heads P.V goes first, because the
       // next head's Q tile is published only after this tile's softmax
       if (!(MH && last_tile)) next_scores();
       // V tile: MN-major, 64-channel atoms KT * 128 bytes apart (LBO), 16 keys (2 KiB) per k-step
       const uint64_t dV = umma_desc_mn_sw128(smem_u32(sKV + stage * 2 * Cfg::KBytes + Cfg::KBytes), KT * 128);
+      mbar_wait(&v_full[stage], phase);
       mbar_wait(p_full, static_cast<uint32_t>(it & 1));
       tcgen05_fence_after();
 #pragma unroll
@@ -315,7 +336,7 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
         umma_f16_ts_warp(tO, ((kPx && kk < 2 && (it & 1)) ? tPx : tP) + 8u * kk, dV + 128u * kk, idesc_o, (j | kk) ? 1u : 0u);
       umma_commit_warp(o_done);
       if (MH && last_tile) next_scores();
-      umma_commit_warp(&kv_empty[stage]);
+      umma_commit_warp(&v_empty[stage]);
       stage = nstage;
       phase = nphase;
     }
