@@ -472,6 +472,8 @@ __global__ void __launch_bounds__(HPB * 32) temporal_attn_fixed_kernel(const __h
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long pix = blockIdx.x;                       // b*HW + hw
   const long long row0 = (pix / HW) * T * HW + pix % HW;  // row of frame 0; frame t adds t*HW
+  griddep_wait();                  // PDL: q, k, v come from the previous kernel of the stream
+  griddep_launch_dependents();
   for (int i = threadIdx.x; i < T * CPR; i += HPB * 32) {
     const int t = i / CPR, c = i - t * CPR;
     const long long row = row0 + static_cast<long long>(t) * HW;
@@ -620,7 +622,7 @@ static int launch_ta_fixed(const __half* q, long long ldq, const __half* k, long
     attr_done[dev].store(true, std::memory_order_release);
   }
   const dim3 grid(static_cast<unsigned>(static_cast<long long>(B) * HW), heads / HPB);
-  temporal_attn_fixed_kernel<D, T, HPB><<<grid, HPB * 32, smem, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, HW, scale_log2);
+  (void)launch_pdl(4, temporal_attn_fixed_kernel<D, T, HPB>, grid, dim3(HPB * 32), smem, st, q, ldq, k, ldk, v, ldv, o, ldo, HW, scale_log2);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_temporal_attention");
   return CCEDIT_OK;
@@ -709,6 +711,8 @@ __global__ void __launch_bounds__(NW * 32, 1) short_kv_attn_kernel(const __grid_
   const int kvi = pair / p.ngroups, grp = pair % p.ngroups;
   const int f_begin = kvi * p.kv_div, f_end = min(p.frames, f_begin + p.kv_div);
   const long long col0 = static_cast<long long>(grp) * G;
+  griddep_wait();                  // PDL: q, k, v come from the previous kernels of the stream
+  griddep_launch_dependents();
   {
     const long long kvf = static_cast<long long>(kvi) * p.kv_mul + p.kv_add;
     const __half* kb = p.k + kvf * p.kv_fs + col0;
@@ -900,7 +904,7 @@ static int launch_sk(const SkParams& p, int grid, cudaStream_t st) {
     }
     attr_done[dev].store(true, std::memory_order_release);
   }
-  short_kv_attn_kernel<D, NKT, NW><<<grid, NW * 32, smem, st>>>(p);
+  (void)launch_pdl(4, short_kv_attn_kernel<D, NKT, NW>, dim3(grid), dim3(NW * 32), smem, st, p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_attention(short kv)");
   return CCEDIT_OK;

@@ -241,6 +241,8 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmK0, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                  // PDL: barriers / TMEM above overlap the previous kernel's tail; its outputs are read below
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer: two cursors, K runs ahead of V =====================
@@ -573,7 +575,7 @@ static int launch_tc2_t(const CUtensorMap* maps, const FaTcParams& p, int frames
     attr_set[dev].store(true, std::memory_order_release);
   }
   dim3 grid((p.lq + kTcTile - 1) / kTcTile, heads / p.hpc, frames);
-  flash_attn_tc2_kernel<KSTEPS, EMU, MH><<<grid, kT2Threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  (void)launch_pdl(2, flash_attn_tc2_kernel<KSTEPS, EMU, MH>, grid, dim3(kT2Threads), smem, st, maps[0], maps[1], maps[2], maps[3], p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_attention(tc2)");
   return CCEDIT_OK;

@@ -48,6 +48,32 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; griddepcontrol.wait blocks until that predecessor has completed
+// and its writes are visible, griddepcontrol.launch_dependents lets the NEXT kernel be scheduled early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int pdl_mask();                // gemm_tc.cu: CCEDIT_PDL bit mask (read once): 1 tap-GEMM, 2 flash attention, 4 short-key / temporal attention, 8 GroupNorm
+inline bool pdl_enabled(int bit = 1) { return (pdl_mask() & bit) != 0; }
+// <<<grid, block, smem, stream>>> with the PDL attribute when enabled; the kernel must call griddep_wait() before it touches
+// anything a predecessor may have written
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int bit, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  const bool on = pdl_enabled(bit);
+  cfg.attrs = on ? &attr : nullptr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // SiLU as x * rcp(1 + 2^(-x log2 e)) on the two approximate MUFU ops (~2 ulp): 5 instructions.  The IEEE '/' drags a
 // slow-path call into every use, and __fdividef adds a range fix-up (FSETP + 2 FMUL) for denominators above 2^126 that
 // 1 + e^-x only reaches where the result is 0 either way (ncu of the GroupNorm kernels: FMUL 21 % of all instructions).

@@ -761,6 +761,12 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (CL >= 2) cluster_sync_all();          // the peer's barriers are initialised before anything can arrive on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touches no global data and may
+  // run while the previous kernel of the stream drains its last tiles; nothing below may start before that kernel has
+  // completed and flushed (both instructions are no-ops for a launch without the attribute).  The dependents of THIS
+  // kernel may be scheduled from here on: they too stop at their own griddepcontrol.wait.
+  griddep_wait();
+  griddep_launch_dependents();
 
   const int kblocks = p.ntaps * p.kchunks;
   const int it0 = CL >= 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -913,6 +919,12 @@ int current_device() {
   int dev = 0;
   return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices ? dev : -1;
 }
+int pdl_mask() {
+  // default 3: tap-GEMM + flash attention.  Measured on one box (ms per sampler step): 0: 214.56, 1: 213.2, 3: 212.8,
+  // 5: 213.9, 9: 215.1 - early-launched GroupNorm / short attention CTAs cost more than their prologues save.
+  static const int m = [] { const char* e = getenv("CCEDIT_PDL"); return e ? atoi(e) : 3; }();
+  return m;
+}
 int device_sm_count() {
   static std::atomic<int> sms[kMaxDevices];
   const int dev = current_device();
@@ -965,23 +977,28 @@ static cudaError_t launch_gemm_t(const CUtensorMap* tm, const GemmKParams& p, in
     cap[dev].store(capacity, std::memory_order_release);
   }
   const int units = work_items < capacity ? work_items : capacity;
-  if (CL == 1) {
-    kern<<<units, kGemmThreads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
-    return cudaGetLastError();
-  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * units);
+  cfg.gridDim = dim3(CL == 1 ? units : 2 * units);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = 2;
-  attr.val.clusterDim.y = 1;
-  attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  if (CL >= 2) {
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = 2;
+    attr[nattr].val.clusterDim.y = 1;
+    attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
+  }
+  if (pdl_enabled(1)) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
   void* args[] = {const_cast<CUtensorMap*>(&tm[0]), const_cast<CUtensorMap*>(&tm[1]), const_cast<CUtensorMap*>(&tm[2]),
                   const_cast<CUtensorMap*>(&tm[3]), const_cast<GemmKParams*>(&p)};
   return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), args);

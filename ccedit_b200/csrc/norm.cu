@@ -194,6 +194,8 @@ __global__ void gn_spatial_fused_kernel(const __half* __restrict__ x, __half* __
   __shared__ float smean[kGroups], srstd[kGroups];
   float* ssum = gn_sm;
   float* ssq = gn_sm + rpi * C;
+  griddep_wait();                  // PDL: x comes from the previous kernel of the stream
+  griddep_launch_dependents();
   const int f = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
   const int cv = threadIdx.x % nvec, r0 = threadIdx.x / nvec;
   const int rows_per_split = (HW + nsplit - 1) / nsplit;
@@ -328,6 +330,8 @@ __global__ void gn_temporal_kernel(const __half* __restrict__ x, __half* __restr
   float* ssum = sg_dyn;
   float* ssq = sg_dyn + ppb * C;
   float* sstat = sg_dyn + 2 * ppb * C;
+  griddep_wait();                  // PDL: x comes from the previous kernel of the stream
+  griddep_launch_dependents();
   const int cv = threadIdx.x % nvec, pl = threadIdx.x / nvec;
   const long long pix = static_cast<long long>(blockIdx.x) * ppb + pl;  // over B*HW
   const bool active = pix < static_cast<long long>(B) * HW;
@@ -551,12 +555,19 @@ extern "C" int ccedit_groupnorm_spatial(const void* x, void* y, const float* gam
         cfg.blockDim = dim3(threads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeCooperative;
-        attr.val.cooperative = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        const cudaError_t le = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(gn_spatial_fused_kernel), args);
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled(8) ? 2 : 1;
+        cudaError_t le = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(gn_spatial_fused_kernel), args);
+        if (le != cudaSuccess && cfg.numAttrs == 2) {          // the two attributes together refused: cooperative alone
+          (void)cudaGetLastError();
+          cfg.numAttrs = 1;
+          le = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(gn_spatial_fused_kernel), args);
+        }
         if (le == cudaSuccess) {
           g_launch_count.fetch_add(1, std::memory_order_relaxed);
           return CCEDIT_OK;
@@ -591,8 +602,9 @@ extern "C" int ccedit_groupnorm_temporal(const void* x, void* y, const float* ga
   const int threads = nvec * ppb;
   const long long npix = static_cast<long long>(B) * HW;
   const int grid = static_cast<int>((npix + ppb - 1) / ppb);
-  gn_temporal_kernel<<<grid, threads, (2 * ppb * C + ppb * 2 * kGroups) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, B, T, HW, C, nvec, ppb, eps, silu);
+  (void)launch_pdl(8, gn_temporal_kernel, dim3(grid), dim3(threads), (2 * ppb * C + ppb * 2 * kGroups) * sizeof(float),
+                   static_cast<cudaStream_t>(stream), static_cast<const __half*>(x), static_cast<__half*>(y), gamma, beta, B, T, HW,
+                   C, nvec, ppb, eps, silu);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   CCEDIT_CUDA_LAUNCH_CHECK("ccedit_groupnorm_temporal");
   return CCEDIT_OK;
