@@ -94,6 +94,7 @@ SIGNATURES = {
     "ccedit_add_center_frame": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "ccedit_to_half": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ccedit_hint_stem01": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "ccedit_hint_stem23": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "ccedit_softmax_rows": (C.c_int, [_vp, _i64, _i64, _i32, _vp]),
     "ccedit_cl_to_ncthw": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i64, _vp]),
     "ccedit_embed_tokens": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -294,6 +294,14 @@ class ControlNet2D(UNetModel):
             w1, b1 = h1._cached((dev, "hs1"), lambda: ops.pack_hint_stem_weight(h1.weight, h1.bias, dev, 16, 144))
             g = ops.hint_stem01(g, w0, b0, w1, b1)
             first = 2
+            h2, h3 = self.input_hint_block[4], self.input_hint_block[6]
+            if (tuple(self.HINT_STRIDES[2:4]) == (2, 1) and tuple(h2.weight.shape[:2]) == (32, 16)
+                    and tuple(h3.weight.shape[:2]) == (32, 32) and g.shape[1] % 2 == 0 and g.shape[2] % 2 == 0):
+                # layers 2 + 3 (16 -> 32 stride 2, 32 -> 32) the same way: no parity split, no 32-channel round trip
+                w2, b2 = h2._cached((dev, "hs2"), lambda: ops.pack_hint_stem_weight(h2.weight, h2.bias, dev, 16, 144))
+                w3, b3 = h3._cached((dev, "hs3"), lambda: ops.pack_hint_stem_weight(h3.weight, h3.bias, dev, 32, 288))
+                g = ops.hint_stem23(g, w2, b2, w3, b3)
+                first = 4
         for i, s in enumerate(self.HINT_STRIDES):
             if i < first:
                 continue

@@ -601,9 +601,9 @@ def to_half(src: torch.Tensor) -> torch.Tensor:
 
 
 def pack_hint_stem_weight(w: torch.Tensor, bias: torch.Tensor, device, cin_pad: int, kpad: int):
-    """Conv2d weight [16, Cin, 3, 3] -> fp16 [16][kpad] with k = tap*cin_pad + channel (tap = kh*3 + kw), fp32 bias."""
+    """Conv2d weight [N, Cin, 3, 3] (N = 16 or 32) -> fp16 [N][kpad] with k = tap*cin_pad + channel (tap = kh*3 + kw), fp32 bias."""
     n, cin = w.shape[0], w.shape[1]
-    if n != 16 or cin > cin_pad or 9 * cin_pad > kpad:
+    if n not in (16, 32) or cin > cin_pad or 9 * cin_pad > kpad:
         raise RuntimeError(f"ccedit_b200.pack_hint_stem_weight: unsupported conv shape {tuple(w.shape)}")
     wp = torch.zeros(n, 9, cin_pad, dtype=torch.float32)
     wp[:, :, :cin] = w.detach().float().cpu().reshape(n, cin, 9).permute(0, 2, 1)
@@ -624,6 +624,20 @@ def hint_stem01(x: torch.Tensor, w0: torch.Tensor, b0: torch.Tensor, w1: torch.T
     _call("hint_stem01", _lib.load().ccedit_hint_stem01,
           (x.data_ptr(), y.data_ptr(), w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), F, H, W, _stream()),
           flops=2.0 * F * H * W * 16 * 9 * (3 + 16), nbytes=_nb(x, y))
+    return y
+
+
+def hint_stem23(x: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor) -> torch.Tensor:
+    """x: [F, H, W, 16] fp16 (H, W even) -> SiLU(conv3x3(SiLU(conv3x3_stride2(x)))) [F, H/2, W/2, 32]: layers 2 and 3 of the
+    ControlNet hint stem in one pass (weights from ``pack_hint_stem_weight`` with (cin_pad, kpad) = (16, 144), (32, 288))."""
+    _require(x, name="x")
+    if not x.is_contiguous() or x.shape[-1] != 16 or x.shape[1] % 2 or x.shape[2] % 2:
+        raise RuntimeError("ccedit_b200.hint_stem23: x must be contiguous [F, H, W, 16] with even H and W")
+    F, H, W, _ = x.shape
+    y = torch.empty(F, H // 2, W // 2, 32, dtype=torch.float16, device=x.device)
+    _call("hint_stem23", _lib.load().ccedit_hint_stem23,
+          (x.data_ptr(), y.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), F, H, W, _stream()),
+          flops=2.0 * F * (H // 2) * (W // 2) * 32 * 9 * (16 + 32), nbytes=_nb(x, y))
     return y
 
 

@@ -194,6 +194,11 @@ int ccedit_to_half(const float* src, void* dst, int64_t n, void* stream);
  * ------------------------------------------------------------------------------------------------------------------ */
 int ccedit_hint_stem01(const void* x, void* y, const void* w0, const float* b0, const void* w1, const float* b1,
                        int32_t F, int32_t H, int32_t W, void* stream);
+/* Layers 2 and 3 of the same stem fused (controlmodel.py:220-223: conv3x3(16->32, stride 2) + SiLU + conv3x3(32->32) + SiLU).
+ * x: [F][H][W][16] fp16 with even H, W (the output of ccedit_hint_stem01), y: [F][H/2][W/2][32] fp16.
+ * w2: fp16 [32][144], k = tap*16 + channel; w3: fp16 [32][288], k = tap*32 + channel (16-byte aligned); b2, b3: fp32 [32]. */
+int ccedit_hint_stem23(const void* x, void* y, const void* w2, const float* b2, const void* w3, const float* b3,
+                       int32_t F, int32_t H, int32_t W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * First stage (VAE): helpers next to ccedit_gemm / ccedit_groupnorm_spatial / ccedit_upsample_nearest2x.

@@ -173,7 +173,7 @@ def test_pack_weight_with_folded_layernorm():
 
 
 def test_pack_hint_stem_weight_layout():
-    """csrc/hint_stem.cu operand layout: [16][kpad] with k = tap * cin_pad + channel, tap = kh * 3 + kw, zero padded."""
+    """csrc/hint_stem.cu operand layout: [N][kpad] with k = tap * cin_pad + channel, tap = kh * 3 + kw, zero padded."""
     g = torch.Generator().manual_seed(6)
     w, b = torch.randn(16, 3, 3, 3, generator=g), torch.randn(16, generator=g)
     wp, bp = ops.pack_hint_stem_weight(w, b, "cpu", 8, 80)
@@ -183,8 +183,13 @@ def test_pack_hint_stem_weight_layout():
         for kw in range(3):
             assert torch.equal(W[:, kh * 3 + kw, :3], w[:, :, kh, kw].half().float())
     assert float(W[:, :9, 3:].abs().max()) == 0 and float(W[:, 9].abs().max()) == 0
+    w3 = torch.randn(32, 32, 3, 3, generator=g)                      # layers 2 / 3: 32 output channels
+    wp3, _ = ops.pack_hint_stem_weight(w3, torch.zeros(32), "cpu", 32, 288)
+    assert wp3.shape == (32, 288) and torch.equal(wp3.float().view(32, 9, 32)[:, 5], w3[:, :, 1, 2].half().float())
     with pytest.raises(RuntimeError):
-        ops.pack_hint_stem_weight(torch.randn(32, 3, 3, 3), torch.randn(32), "cpu", 8, 80)
+        ops.pack_hint_stem_weight(torch.randn(48, 3, 3, 3), torch.randn(48), "cpu", 8, 80)
+    with pytest.raises(RuntimeError):
+        ops.pack_hint_stem_weight(torch.randn(16, 16, 3, 3), torch.randn(16), "cpu", 8, 80)   # more channels than cin_pad
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -192,6 +192,22 @@ def test_hint_stem_first_two_layers_fused(ops, Fr, H, W):
     close(out.permute(0, 3, 1, 2), ref, f"hint stem layers 0+1 {Fr}x{H}x{W}")
 
 
+@pytest.mark.parametrize("Fr,H,W", [(2, 32, 128), (1, 40, 70), (3, 16, 64), (1, 6, 10), (1, 2, 2)])
+def test_hint_stem_layers_two_and_three_fused(ops, Fr, H, W):
+    """controlmodel.py:220-223: conv3x3(16->32, stride 2)+SiLU+conv3x3(32->32)+SiLU in one kernel (csrc/hint_stem.cu),
+    ragged tiles, image borders inside and outside the halo."""
+    x = rnd(Fr, 16, H, W, seed=65)
+    w2, b2 = rnd(32, 16, 3, 3, seed=66, scale=1 / math.sqrt(144)), rnd(32, seed=67).float()
+    w3, b3 = rnd(32, 32, 3, 3, seed=68, scale=1 / math.sqrt(288)), rnd(32, seed=69).float()
+    p2 = ops.pack_hint_stem_weight(w2.float(), b2, "cuda", 16, 144)
+    p3 = ops.pack_hint_stem_weight(w3.float(), b3, "cuda", 32, 288)
+    out = ops.hint_stem23(x.permute(0, 2, 3, 1).contiguous().cuda(), *p2, *p3)
+    mid = F.silu(F.conv2d(x.float(), w2.float(), b2, stride=2, padding=1)).half().float()   # the kernel keeps layer 2 in fp16
+    ref = F.silu(F.conv2d(mid, w3.float(), b3, padding=1))
+    assert tuple(out.shape) == (Fr, H // 2, W // 2, 32)
+    close(out.permute(0, 3, 1, 2), ref, f"hint stem layers 2+3 {Fr}x{H}x{W}")
+
+
 def test_conv3x3_time_embedding_rows_with_padded_tiles(ops):
     """34 frames of 2x2 pixels: the 128-row tiles pad the frame axis to 64, and the padded rows must not index past the
     [B, Cout] time-embedding rows (regression: an out-of-bounds read in the epilogue's bias staging)."""
