@@ -132,7 +132,9 @@ hint_stem01_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
             for (int nt = 0; nt < 2; ++nt) {
               const float v0 = in ? silu_f(acc[u][nt][2 * hh] + bias0[nt][0]) : 0.f;
               const float v1 = in ? silu_f(acc[u][nt][2 * hh + 1] + bias0[nt][1]) : 0.f;
-              *reinterpret_cast<uint32_t*>(s_mid + q * 32 + (nt * 8 + 2 * t) * 2) = hs_pack(v0, v1);
+              // 16-byte half of the pixel XOR-ed with bit 2 of the pixel index: layer 1's ldmatrix rows (consecutive
+              // 32-byte pixels) then fall into eight different 16-byte slots of a 128-byte line (was a 2-way conflict)
+              *reinterpret_cast<uint32_t*>(s_mid + q * 32 + ((nt ^ ((q >> 2) & 1)) << 4) + 4 * t) = hs_pack(v0, v1);
             }
           }
         }
@@ -144,7 +146,7 @@ hint_stem01_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
   // ---- 3. layer 1: m-tile = 16 pixels of one output row; one tap (16 channels) per k-step ----
   {
     const int lpx = (lane & 7) + ((lane >> 3) & 1) * 8;    // pixel inside the m-tile
-    const int lch = (lane >> 4) * 16;                      // channel half (bytes)
+    const int lhalf = lane >> 4;                           // channel half
     constexpr int kU = 1;
     for (int mt0 = warp; mt0 < kHsTH * (kHsTW / 16); mt0 += kU * (kHsThreads / 32)) {
       int ry[kU], cx[kU];
@@ -161,7 +163,8 @@ hint_stem01_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           uint32_t a[4];
-          ldmatrix_x4(a, smem_u32(s_mid + ((ry[u] + ty) * kHsMW + cx[u] + lpx + tx) * 32 + lch));
+          const int q = (ry[u] + ty) * kHsMW + cx[u] + lpx + tx;
+          ldmatrix_x4(a, smem_u32(s_mid + q * 32 + ((lhalf ^ ((q >> 2) & 1)) << 4)));
           mma_m16n8k16(acc[u][0], a, wf1[ks][0]);
           mma_m16n8k16(acc[u][1], a, wf1[ks][1]);
         }
@@ -207,11 +210,17 @@ hint_stem01_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
 //      memory (padded rows: conflict-free fragment loads); bias + SiLU; staged over the dead input window and written as
 //      whole 2 KB rows.
 // Layer-2 weights live in registers as mma B fragments (72 per thread).  H and W must be even.
+// Shared-memory layouts (ncu of the first version: 44 M bank conflicts, shared-memory pipe 73 % busy, mio_throttle 4.8
+// per issue - an ldmatrix 8 x 8 fetch wants its eight 16-byte rows in eight different 16-byte slots of a 128-byte line):
+//   * input window: even and odd columns in separate planes ([row][parity][column / 2][16 ch]), so that the stride-2
+//     taps read consecutive 32-byte pixels, and the 16-byte half of a pixel XOR-ed with bit 2 of the plane column;
+//   * layer-2 halo (64 bytes per pixel): the 16-byte chunk XOR-ed with bits 1-2 of the linear pixel index.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kH2TH = 8, kH2TW = 32;                        // output tile (half resolution)
 constexpr int kH2MH = kH2TH + 2, kH2MW = kH2TW + 2;         // layer-2 output (layer-3 input) halo tile
 constexpr int kH2IH = 2 * kH2MH + 1, kH2IW = 2 * kH2MW + 1; // input window (full resolution)
-constexpr int kH2InBytes = kH2IH * kH2IW * 32;              // 16 fp16 channels per pixel
+constexpr int kH2PW = (kH2IW + 1) / 2;                      // columns per parity plane of the input window
+constexpr int kH2InBytes = kH2IH * 2 * kH2PW * 32;          // 16 fp16 channels per pixel
 constexpr int kH2MidBytes = kH2MH * kH2MW * 64;             // 32 fp16 channels per pixel
 constexpr int kH2K2 = 144, kH2K3 = 288, kH2W3Stride = kH2K3 + 8;   // halves; +8: fragment loads hit 32 different banks
 constexpr int kH2W3Bytes = 32 * kH2W3Stride * 2;
@@ -238,7 +247,9 @@ hint_stem23_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
     const int iy = pix / kH2IW, ix = pix - iy * kH2IW;
     const int gy = 2 * y0 - 3 + iy, gx = 2 * x0 - 3 + ix;
     const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-    cp_async_16(smem_u32(s_in + pix * 32 + half * 16), xf + (static_cast<long long>(ok ? gy : 0) * W + (ok ? gx : 0)) * 16 + half * 8, ok);
+    const int col = ix >> 1;
+    cp_async_16(smem_u32(s_in + ((iy * 2 + (ix & 1)) * kH2PW + col) * 32 + ((half ^ ((col >> 2) & 1)) << 4)),
+                xf + (static_cast<long long>(ok ? gy : 0) * W + (ok ? gx : 0)) * 16 + half * 8, ok);
   }
   cp_async_commit();
   // layer-3 weights -> shared memory (rows of 288 halves, padded to 296)
@@ -272,18 +283,22 @@ hint_stem23_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
     constexpr int npix = kH2MH * kH2MW;
     constexpr int ntile = (npix + 15) / 16;
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;    // ldmatrix.x4: pixel of the m-tile this lane addresses
-    const int lch = (lane >> 4) * 16;                       // channel half (bytes)
+    const int lhalf = lane >> 4;                            // channel half
     for (int mt = warp; mt < ntile; mt += kHsThreads / 32) {
       int p = mt * 16 + lrow;
       p = p < npix ? p : npix - 1;
       const int py = p / kH2MW, px = p - py * kH2MW;
-      const uint32_t abase = smem_u32(s_in + ((2 * py) * kH2IW + 2 * px) * 32 + lch);
+      // input pixel (2 py + ty, 2 px + tx): plane tx & 1, plane column px + (tx >> 1)
+      const uint32_t row0 = smem_u32(s_in) + static_cast<uint32_t>((2 * py) * 2 * kH2PW) * 32u;
+      uint32_t acol[2];                                     // byte offset of plane column px / px + 1 incl. the swizzled half
+#pragma unroll
+      for (int j = 0; j < 2; ++j) acol[j] = static_cast<uint32_t>((px + j) * 32 + ((lhalf ^ (((px + j) >> 2) & 1)) << 4));
       float acc[4][4] = {};
 #pragma unroll
       for (int ks = 0; ks < 9; ++ks) {
         const int ty = ks / 3, tx = ks - ty * 3;
         uint32_t a[4];
-        ldmatrix_x4(a, abase + (ty * kH2IW + tx) * 32);
+        ldmatrix_x4(a, row0 + static_cast<uint32_t>((ty * 2 + (tx & 1)) * kH2PW * 32) + acol[tx >> 1]);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) mma_m16n8k16(acc[nt], a, wf2[ks][nt]);
       }
@@ -298,7 +313,7 @@ hint_stem23_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
           for (int nt = 0; nt < 4; ++nt) {
             const float v0 = in ? silu_f(acc[nt][2 * hh] + bias2[nt][0]) : 0.f;
             const float v1 = in ? silu_f(acc[nt][2 * hh + 1] + bias2[nt][1]) : 0.f;
-            *reinterpret_cast<uint32_t*>(s_mid + q * 64 + (nt * 8 + 2 * t) * 2) = hs_pack(v0, v1);
+            *reinterpret_cast<uint32_t*>(s_mid + q * 64 + ((nt ^ ((q >> 1) & 3)) << 4) + 4 * t) = hs_pack(v0, v1);
           }
         }
       }
@@ -309,19 +324,19 @@ hint_stem23_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
   // ---- 3. layer 3: m-tile = 16 pixels of one output row; 18 k-steps = 9 taps x two 16-channel halves ----
   {
     const int lpx = (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int lch = (lane >> 4) * 16;
+    const int lhalf = lane >> 4;
     constexpr int ntile = kH2TH * (kH2TW / 16);              // 16: two per warp, processed together (B fragments shared)
     static_assert(ntile == 2 * (kHsThreads / 32), "two m-tiles per warp");
-    int ry[2], cx[2];
-    uint32_t abase[2];
+    int ry[2], cx[2], pbase[2];
     float acc[2][4][4] = {};
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int mt = warp + u * (kHsThreads / 32);
       ry[u] = mt / (kH2TW / 16);
       cx[u] = (mt - ry[u] * (kH2TW / 16)) * 16;
-      abase[u] = smem_u32(s_mid + (ry[u] * kH2MW + cx[u] + lpx) * 64 + lch);
+      pbase[u] = ry[u] * kH2MW + cx[u] + lpx;               // linear halo pixel of this lane's row for tap (0, 0)
     }
+    const uint32_t smid = smem_u32(s_mid);
 #pragma unroll
     for (int ks = 0; ks < 18; ++ks) {
       const int tap = ks >> 1, kc = ks & 1;
@@ -336,7 +351,8 @@ hint_stem23_kernel(const __half* __restrict__ x, __half* __restrict__ y, const _
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         uint32_t a[4];
-        ldmatrix_x4(a, abase[u] + (ty * kH2MW + tx) * 64 + kc * 32);
+        const int q = pbase[u] + ty * kH2MW + tx;                                    // halo pixel; chunk = 2 kc + half
+        ldmatrix_x4(a, smid + static_cast<uint32_t>(q * 64 + (((2 * kc + lhalf) ^ ((q >> 1) & 3)) << 4)));
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) mma_m16n8k16(acc[u][nt], a, bf[nt]);
       }
