@@ -651,16 +651,21 @@ int attention_tc(const ccedit_attn_desc* a, cudaStream_t st) {
     const char* e = getenv("CCEDIT_ATTN_EMU");
     return e ? atoi(e) : kTcDefaultEmu;
   }();
+  static const bool emu_wide = [] { const char* e = getenv("CCEDIT_ATTN_EMU"); return e && atoi(e) != 0; }();
   switch (ks) {
     case 1: return launch_tc2<1, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
     case 2: return launch_tc2<2, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
     case 3: return emu == 0 ? launch_tc2<3, 0>(maps, p, a->frames, a->heads, st)
                             : launch_tc2<3, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
     case 4: return launch_tc2<4, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
-    case 5: return launch_tc2<5, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
+    // d = 80 / 160 (the network's other two widths): 64-key tiles, half the exponentials per tile - the MUFU pipe is not
+    // what limits them, the FMA-pipe exponentials only add instructions (CCEDIT_ATTN_EMU=1 keeps them: A/B)
+    case 5: return emu_wide ? launch_tc2<5, kTcDefaultEmu>(maps, p, a->frames, a->heads, st)
+                            : launch_tc2<5, 0>(maps, p, a->frames, a->heads, st);
     case 6: return launch_tc2<6, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
     case 8: return launch_tc2<8, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
-    default: return launch_tc2<10, kTcDefaultEmu>(maps, p, a->frames, a->heads, st);
+    default: return emu_wide ? launch_tc2<10, kTcDefaultEmu>(maps, p, a->frames, a->heads, st)
+                             : launch_tc2<10, 0>(maps, p, a->frames, a->heads, st);
   }
 }
 
